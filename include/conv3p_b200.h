@@ -1,0 +1,171 @@
+/* conv3p_b200.h -- C ABI of libconv3p_b200.so: the Conv3p pointwise-convolution operator
+ * (forward + Conv3pGrad) for NVIDIA B200 (sm_100a).
+ *
+ * Drop-in boundary.  These entry points are what a binding of the reference operator would call
+ * instead of the reference's TensorFlow kernels:
+ *
+ *   reference interface (hkust-vgd/pointwise)                      replaced by
+ *   -------------------------------------------------------------  ---------------------------
+ *   REGISTER_OP("Conv3p")      tf_ops/conv3p/register_op.cpp:44-61  conv3p_op_forward_f32
+ *   REGISTER_OP("Conv3pGrad")  tf_ops/conv3p/register_op.cpp:63-75  conv3p_op_backward_f32
+ *   Conv3pOp<GPU>::Compute     tf_conv3p_atrous.cu:541-641          conv3p_plan_build_f32 + conv3p_forward_f32
+ *   Conv3pGradOp<GPU>::Compute tf_conv3p_atrous.cu:659-774          conv3p_plan_build_backward + conv3p_backward_f32
+ *   Grid::build_neighbor_count tf_conv3p_atrous.cu:288-327          conv3p_plan_build_f32 (count table inside the plan)
+ *   session.run feed/fetch     train_modelnet40_acsd.py:132         conv3p_host_forward_f32 / conv3p_host_backward_f32
+ *
+ * Conventions (identical to the reference, tf_conv3p_atrous.cpp:409-444, :490):
+ *   points  [B,N,3]   float32 row-major           input   [B,N,Cin]  float32
+ *   filter  [3,3,3,Cin,Cout] float32, dims ordered z,y,x; weight index (f*Cin+k)*Cout+c,
+ *           f = (fz*3+fy)*3+fx                    output  [B,N,Cout] float32
+ *   stride  int[3] in x,y,z order                 voxel_size  float
+ * Only 3x3x3 filters (every reference model) and float32 are supported.
+ *
+ * Memory: the library never allocates device memory.  The caller owns inputs, outputs, the plan
+ * buffer and the scratch buffer (sizes from the *_bytes functions).  Outputs are fully overwritten.
+ * Streams: everything is enqueued on the caller's stream; no entry point synchronises the host
+ * except conv3p_plan_stats and the conv3p_host_* convenience calls (which say so).
+ * Errors: every entry point returns a status code (0 = OK); the library never exits the process
+ * (contrast tf_conv3p_atrous.cu:46-54).  All pointers except where noted are DEVICE pointers.
+ */
+#ifndef CONV3P_B200_H_
+#define CONV3P_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* conv3p_stream_t; /* == cudaStream_t */
+
+enum {
+  CONV3P_OK = 0,
+  CONV3P_ERR_INVALID_ARGUMENT = 1, /* shapes / strides / voxel size rejected */
+  CONV3P_ERR_BUFFER_TOO_SMALL = 2, /* plan or scratch buffer smaller than *_bytes() */
+  CONV3P_ERR_CUDA = 3,             /* a CUDA runtime call failed; see conv3p_last_cuda_error */
+  CONV3P_ERR_UNSUPPORTED = 4,      /* e.g. filter not 3x3x3 */
+  CONV3P_ERR_PAIR_OVERFLOW = 5,    /* reported by conv3p_plan_stats: pair_capacity too small */
+  CONV3P_ERR_NO_BACKWARD_LISTS = 6 /* backward called before conv3p_plan_build_backward */
+};
+
+/* Geometry of one call: B clouds of N points, the dilation stride per axis (x,y,z), the voxel size
+ * and the capacity of the neighbour-pair lists.  pair_capacity bounds the TOTAL number of
+ * (point, neighbour) pairs over the whole batch; conv3p_plan_stats reports the number needed. */
+typedef struct {
+  int B;
+  int N;
+  int stride[3];
+  float voxel_size;
+  long long pair_capacity;
+} conv3p_geom_t;
+
+/* Result of conv3p_plan_stats (host memory). */
+typedef struct {
+  long long total_pairs;    /* forward (i, j) pairs found == sum of the count table */
+  long long backward_pairs; /* pairs kept by the backward rule (0 until build_backward ran) */
+  int overflow;             /* 1 if total_pairs > pair_capacity: lists are incomplete, rebuild */
+  int has_backward;
+} conv3p_plan_stats_t;
+
+/* Byte offsets of the plan's arrays inside the plan buffer (for parity tests and debugging).
+ * count_table is exactly the reference's neighbor_count table [B*N, 27] int32
+ * (tf_conv3p_atrous.cpp:369-379). */
+typedef struct {
+  size_t header;       /* int64[16] device-side counters                                   */
+  size_t cloud_meta;   /* float[B][8]: vmin xyz, voxel, then dims x,y,z and key bits as int */
+  size_t sorted_key;   /* uint32[B*N] voxel keys in sorted order                            */
+  size_t sorted_xyzi;  /* float4[B*N]  (x, y, z, bit-cast original index) in sorted order   */
+  size_t count_table;  /* int32[B*N][27] by original point                                  */
+  size_t pair_begin;   /* int64[B*N] start of each point's list                             */
+  size_t pair_len;     /* int32[B*N] forward list length K_i                                */
+  size_t pair_row;     /* int32[capacity] neighbour rows b*N+j, grouped by ascending cell f */
+  size_t bwd_count;    /* int32[B*N][27] backward list cell counts                          */
+  size_t bwd_row;      /* int32[capacity] rows b*N+ii                                       */
+  size_t bwd_weight;   /* float[capacity] 1/count(ii, f')                                   */
+  size_t sort_tmp;     /* scratch of the radix sort                                         */
+  size_t total_bytes;
+} conv3p_plan_layout_t;
+
+/* ---- neighbour plan: voxel-key radix sort + windowed exact-predicate search ------------------ */
+
+size_t conv3p_plan_bytes(const conv3p_geom_t* geom);
+int conv3p_plan_layout(const conv3p_geom_t* geom, conv3p_plan_layout_t* out /* host */);
+
+/* Builds the forward neighbour structure of `points` into `plan` (device, >= conv3p_plan_bytes):
+ * per-cloud bounding box, voxel keys, radix sort, per-point windowed search with the reference's
+ * exact predicate (tf_conv3p_atrous.cpp:232-301), count table and cell-grouped neighbour lists. */
+int conv3p_plan_build_f32(const conv3p_geom_t* geom, const float* points, void* plan,
+                          size_t plan_bytes, conv3p_stream_t stream);
+
+/* Adds the backward lists: for every j and every ii in N(j), the cell f' of j in ii's frame without
+ * a box test, dropped when it is a hole or count(ii, f') == 0 (tf_conv3p_atrous.cpp:654-679). */
+int conv3p_plan_build_backward(const conv3p_geom_t* geom, const float* points, void* plan,
+                               size_t plan_bytes, conv3p_stream_t stream);
+
+/* Copies the plan's counters to the host.  SYNCHRONISES `stream`. */
+int conv3p_plan_stats(const conv3p_geom_t* geom, const void* plan, conv3p_plan_stats_t* out /* host */,
+                      conv3p_stream_t stream);
+
+/* ---- the operator on a built plan ------------------------------------------------------------- */
+
+size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout);
+
+/* output[B,N,Cout] = Conv3p(points, input, filter); follows tf_conv3p_atrous.cpp:456-504. */
+int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
+                       const float* filter, int Cin, int Cout, float* output, void* scratch,
+                       size_t scratch_bytes, conv3p_stream_t stream);
+
+/* grad_input[B,N,Cin], grad_filter[27,Cin,Cout]; follows tf_conv3p_atrous.cpp:622-716.
+ * Either output pointer may be NULL to skip it.  grad_filter is reduced in a fixed order
+ * (deterministic; the reference's OpenMP/atomicAdd reductions are not). */
+int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float* grad_output,
+                        const float* input, const float* filter, int Cin, int Cout,
+                        float* grad_input, float* grad_filter, void* scratch, size_t scratch_bytes,
+                        conv3p_stream_t stream);
+
+/* ---- one-shot operator calls with the reference's Compute() shape ----------------------------- */
+/* workspace >= conv3p_op_workspace_bytes(); holds plan + scratch.  filter_dims = {fz,fy,fx}. */
+size_t conv3p_op_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout);
+
+int conv3p_op_forward_f32(const float* points, const float* input, const float* filter,
+                          const int filter_dims[3], const int stride_xyz[3], float voxel_size, int B,
+                          int N, int Cin, int Cout, long long pair_capacity, float* output,
+                          void* workspace, size_t workspace_bytes, conv3p_stream_t stream);
+
+int conv3p_op_backward_f32(const float* grad_output, const float* points, const float* input,
+                           const float* filter, const int filter_dims[3], const int stride_xyz[3],
+                           float voxel_size, int B, int N, int Cin, int Cout,
+                           long long pair_capacity, float* grad_input, float* grad_filter,
+                           void* workspace, size_t workspace_bytes, conv3p_stream_t stream);
+
+/* ---- host-buffer calls (the reference's feed/fetch shape) -------------------------------------- */
+/* All tensor pointers are HOST pointers (pinned memory gives asynchronous copies); `workspace` is
+ * DEVICE memory >= conv3p_host_workspace_bytes().  Copies inputs host->device, runs the operator,
+ * copies results device->host and SYNCHRONISES `stream` before returning. */
+size_t conv3p_host_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout);
+
+int conv3p_host_forward_f32(const float* h_points, const float* h_input, const float* h_filter,
+                            const int stride_xyz[3], float voxel_size, int B, int N, int Cin,
+                            int Cout, long long pair_capacity, float* h_output, void* workspace,
+                            size_t workspace_bytes, conv3p_stream_t stream);
+
+int conv3p_host_backward_f32(const float* h_grad_output, const float* h_points,
+                             const float* h_input, const float* h_filter, const int stride_xyz[3],
+                             float voxel_size, int B, int N, int Cin, int Cout,
+                             long long pair_capacity, float* h_grad_input, float* h_grad_filter,
+                             void* workspace, size_t workspace_bytes, conv3p_stream_t stream);
+
+/* ---- diagnostics -------------------------------------------------------------------------------- */
+const char* conv3p_status_string(int status);
+const char* conv3p_last_cuda_error(void); /* thread-local text of the last CONV3P_ERR_CUDA */
+int conv3p_abi_version(void);
+/* Number of kernels this library launched on behalf of the calling thread since the last reset. */
+long long conv3p_launch_count(int reset);
+/* Selects the contraction engine: 0 = auto, 1 = fp32 SIMT only, 2 = tensor cores (3xTF32) where
+ * supported.  Returns the previous value.  Process-wide. */
+int conv3p_set_engine(int engine);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONV3P_B200_H_ */

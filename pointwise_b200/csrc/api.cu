@@ -1,0 +1,383 @@
+// api.cu -- the C ABI of libconv3p_b200.so (declared in include/conv3p_b200.h).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace c3p {
+
+static thread_local char g_cuda_error[512] = "";
+static thread_local long long g_launches = 0;
+static std::atomic<int> g_engine{0};
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s (%s)", what, cudaGetErrorName(e),
+           cudaGetErrorString(e));
+  (void)cudaGetLastError();
+  return CONV3P_ERR_CUDA;
+}
+void count_launch(int n) { g_launches += n; }
+int engine() { return g_engine.load(); }
+
+int check_geom(const conv3p_geom_t* g) {
+  if (!g) return CONV3P_ERR_INVALID_ARGUMENT;
+  if (g->B < 0 || g->N < 0 || g->N >= (1 << 27)) return CONV3P_ERR_INVALID_ARGUMENT;
+  if ((long long)g->B * g->N >= (1LL << 31)) return CONV3P_ERR_INVALID_ARGUMENT;
+  for (int a = 0; a < 3; ++a)
+    if (g->stride[a] < 1 || g->stride[a] > 4096) return CONV3P_ERR_INVALID_ARGUMENT;
+  if (!(g->voxel_size > 0.0f) || !(g->voxel_size < 1e30f)) return CONV3P_ERR_INVALID_ARGUMENT;
+  if (g->pair_capacity < 0) return CONV3P_ERR_INVALID_ARGUMENT;
+  return CONV3P_OK;
+}
+
+int compute_layout(const conv3p_geom_t* g, conv3p_plan_layout_t* L) {
+  int st = check_geom(g);
+  if (st) return st;
+  const size_t pts = (size_t)g->B * g->N;
+  const size_t cap = (size_t)g->pair_capacity;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o += align_up(bytes);
+    return at;
+  };
+  L->header = take(sizeof(long long) * H_SLOTS);
+  L->cloud_meta = take(sizeof(float) * 8 * (size_t)g->B);
+  L->sorted_key = take(sizeof(uint32_t) * pts);
+  L->sorted_xyzi = take(sizeof(float4) * pts);
+  L->count_table = take(sizeof(int) * pts * C3P_NCELL);
+  L->pair_begin = take(sizeof(long long) * pts);
+  L->pair_len = take(sizeof(int) * pts);
+  L->pair_row = take(sizeof(int) * cap);
+  L->bwd_count = take(sizeof(int) * pts * C3P_NCELL);
+  L->bwd_row = take(sizeof(int) * cap);
+  L->bwd_weight = take(sizeof(float) * cap);
+  L->sort_tmp = take(sizeof(uint32_t) * 4 * pts);
+  L->total_bytes = o;
+  return CONV3P_OK;
+}
+
+int make_view(const conv3p_geom_t* g, const void* plan, size_t plan_bytes, PlanView* v) {
+  conv3p_plan_layout_t L;
+  int st = compute_layout(g, &L);
+  if (st) return st;
+  if (!plan || plan_bytes < L.total_bytes) return CONV3P_ERR_BUFFER_TOO_SMALL;
+  if (reinterpret_cast<uintptr_t>(plan) % 16 != 0) return CONV3P_ERR_INVALID_ARGUMENT;
+  char* p = static_cast<char*>(const_cast<void*>(plan));
+  v->header = reinterpret_cast<long long*>(p + L.header);
+  v->cloud_meta = reinterpret_cast<float*>(p + L.cloud_meta);
+  v->sorted_key = reinterpret_cast<uint32_t*>(p + L.sorted_key);
+  v->sorted_xyzi = reinterpret_cast<float4*>(p + L.sorted_xyzi);
+  v->count_table = reinterpret_cast<int*>(p + L.count_table);
+  v->pair_begin = reinterpret_cast<long long*>(p + L.pair_begin);
+  v->pair_len = reinterpret_cast<int*>(p + L.pair_len);
+  v->pair_row = reinterpret_cast<int*>(p + L.pair_row);
+  v->bwd_count = reinterpret_cast<int*>(p + L.bwd_count);
+  v->bwd_row = reinterpret_cast<int*>(p + L.bwd_row);
+  v->bwd_weight = reinterpret_cast<float*>(p + L.bwd_weight);
+  v->sort_tmp = reinterpret_cast<uint32_t*>(p + L.sort_tmp);
+  return CONV3P_OK;
+}
+
+static int check_channels(int Cin, int Cout) {
+  if (Cin < 1 || Cout < 1 || Cin > (1 << 16) || Cout > (1 << 16)) return CONV3P_ERR_INVALID_ARGUMENT;
+  return CONV3P_OK;
+}
+
+static conv3p_geom_t make_geom(int B, int N, const int stride[3], float voxel, long long cap) {
+  conv3p_geom_t g;
+  g.B = B; g.N = N;
+  g.stride[0] = stride ? stride[0] : 0;
+  g.stride[1] = stride ? stride[1] : 0;
+  g.stride[2] = stride ? stride[2] : 0;
+  g.voxel_size = voxel;
+  g.pair_capacity = cap;
+  return g;
+}
+
+}  // namespace c3p
+
+using namespace c3p;
+
+extern "C" {
+
+int conv3p_abi_version(void) { return 1; }
+
+const char* conv3p_status_string(int s) {
+  switch (s) {
+    case CONV3P_OK: return "ok";
+    case CONV3P_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case CONV3P_ERR_BUFFER_TOO_SMALL: return "plan/scratch/workspace buffer too small";
+    case CONV3P_ERR_CUDA: return "CUDA runtime error";
+    case CONV3P_ERR_UNSUPPORTED: return "unsupported configuration (only 3x3x3 float32 filters)";
+    case CONV3P_ERR_PAIR_OVERFLOW: return "pair_capacity too small for this batch";
+    case CONV3P_ERR_NO_BACKWARD_LISTS: return "backward lists not built";
+    default: return "unknown status";
+  }
+}
+
+const char* conv3p_last_cuda_error(void) { return g_cuda_error; }
+
+long long conv3p_launch_count(int reset) {
+  long long n = g_launches;
+  if (reset) g_launches = 0;
+  return n;
+}
+
+int conv3p_set_engine(int e) { return g_engine.exchange(e); }
+
+size_t conv3p_plan_bytes(const conv3p_geom_t* geom) {
+  conv3p_plan_layout_t L;
+  if (compute_layout(geom, &L)) return 0;
+  return L.total_bytes;
+}
+
+int conv3p_plan_layout(const conv3p_geom_t* geom, conv3p_plan_layout_t* out) {
+  if (!out) return CONV3P_ERR_INVALID_ARGUMENT;
+  return compute_layout(geom, out);
+}
+
+int conv3p_plan_build_f32(const conv3p_geom_t* geom, const float* points, void* plan,
+                          size_t plan_bytes, conv3p_stream_t stream) {
+  PlanView v;
+  int st = make_view(geom, plan, plan_bytes, &v);
+  if (st) return st;
+  if (!points && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
+  st = launch_cloud_sort(geom, points, v, stream);
+  if (st) return st;
+  return launch_neighbor_search(geom, v, stream);
+}
+
+int conv3p_plan_build_backward(const conv3p_geom_t* geom, const float* points, void* plan,
+                               size_t plan_bytes, conv3p_stream_t stream) {
+  PlanView v;
+  int st = make_view(geom, plan, plan_bytes, &v);
+  if (st) return st;
+  st = launch_backward_lists(geom, points, v, stream);
+  if (st) return st;
+  C3P_CUDA(cudaMemsetAsync(v.header + H_HAS_BWD, 1, sizeof(long long), stream));
+  return CONV3P_OK;
+}
+
+int conv3p_plan_stats(const conv3p_geom_t* geom, const void* plan, conv3p_plan_stats_t* out,
+                      conv3p_stream_t stream) {
+  if (!out) return CONV3P_ERR_INVALID_ARGUMENT;
+  conv3p_plan_layout_t L;
+  int st = compute_layout(geom, &L);
+  if (st) return st;
+  if (!plan) return CONV3P_ERR_INVALID_ARGUMENT;
+  long long h[H_SLOTS];
+  C3P_CUDA(cudaMemcpyAsync(h, static_cast<const char*>(plan) + L.header, sizeof(h),
+                           cudaMemcpyDeviceToHost, stream));
+  C3P_CUDA(cudaStreamSynchronize(stream));
+  out->total_pairs = h[H_CURSOR];
+  out->backward_pairs = h[H_BWD_PAIRS];
+  out->overflow = (h[H_OVERFLOW] != 0 || h[H_CURSOR] > geom->pair_capacity) ? 1 : 0;
+  out->has_backward = h[H_HAS_BWD] != 0;
+  return CONV3P_OK;
+}
+
+size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
+  if (check_geom(geom) || check_channels(Cin, Cout)) return 0;
+  return backward_filter_scratch_bytes(geom, Cin, Cout) + 256;
+}
+
+int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
+                       const float* filter, int Cin, int Cout, float* output, void* scratch,
+                       size_t scratch_bytes, conv3p_stream_t stream) {
+  (void)scratch; (void)scratch_bytes;
+  int st = check_channels(Cin, Cout);
+  if (st) return st;
+  PlanView v;
+  st = make_view(geom, plan, conv3p_plan_bytes(geom), &v);
+  if (st) return st;
+  if ((long long)geom->B * geom->N == 0) return CONV3P_OK;
+  if (!input || !filter || !output) return CONV3P_ERR_INVALID_ARGUMENT;
+  return launch_forward_simt(geom, v, input, filter, Cin, Cout, output, stream);
+}
+
+int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float* grad_output,
+                        const float* input, const float* filter, int Cin, int Cout,
+                        float* grad_input, float* grad_filter, void* scratch, size_t scratch_bytes,
+                        conv3p_stream_t stream) {
+  int st = check_channels(Cin, Cout);
+  if (st) return st;
+  PlanView v;
+  st = make_view(geom, plan, conv3p_plan_bytes(geom), &v);
+  if (st) return st;
+  if (!grad_output && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
+  if (grad_input) {
+    if (!filter) return CONV3P_ERR_INVALID_ARGUMENT;
+    st = launch_backward_input_simt(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);
+    if (st) return st;
+  }
+  if (grad_filter) {
+    if (!input && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
+    st = launch_backward_filter_simt(geom, v, grad_output, input, Cin, Cout, grad_filter, scratch,
+                                     scratch_bytes, stream);
+    if (st) return st;
+  }
+  return CONV3P_OK;
+}
+
+// ---- one-shot calls ------------------------------------------------------------------------------
+
+size_t conv3p_op_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
+  size_t p = conv3p_plan_bytes(geom);
+  if (!p) return 0;
+  return p + conv3p_scratch_bytes(geom, Cin, Cout);
+}
+
+static int check_filter_dims(const int filter_dims[3]) {
+  if (!filter_dims) return CONV3P_ERR_INVALID_ARGUMENT;
+  if (filter_dims[0] != 3 || filter_dims[1] != 3 || filter_dims[2] != 3) return CONV3P_ERR_UNSUPPORTED;
+  return CONV3P_OK;
+}
+
+int conv3p_op_forward_f32(const float* points, const float* input, const float* filter,
+                          const int filter_dims[3], const int stride_xyz[3], float voxel_size, int B,
+                          int N, int Cin, int Cout, long long pair_capacity, float* output,
+                          void* workspace, size_t workspace_bytes, conv3p_stream_t stream) {
+  int st = check_filter_dims(filter_dims);
+  if (st) return st;
+  if (!stride_xyz) return CONV3P_ERR_INVALID_ARGUMENT;
+  conv3p_geom_t g = make_geom(B, N, stride_xyz, voxel_size, pair_capacity);
+  st = check_geom(&g);
+  if (st) return st;
+  const size_t pb = conv3p_plan_bytes(&g);
+  if (!workspace || workspace_bytes < conv3p_op_workspace_bytes(&g, Cin, Cout))
+    return CONV3P_ERR_BUFFER_TOO_SMALL;
+  st = conv3p_plan_build_f32(&g, points, workspace, pb, stream);
+  if (st) return st;
+  return conv3p_forward_f32(&g, workspace, input, filter, Cin, Cout, output,
+                            static_cast<char*>(workspace) + pb, workspace_bytes - pb, stream);
+}
+
+int conv3p_op_backward_f32(const float* grad_output, const float* points, const float* input,
+                           const float* filter, const int filter_dims[3], const int stride_xyz[3],
+                           float voxel_size, int B, int N, int Cin, int Cout,
+                           long long pair_capacity, float* grad_input, float* grad_filter,
+                           void* workspace, size_t workspace_bytes, conv3p_stream_t stream) {
+  int st = check_filter_dims(filter_dims);
+  if (st) return st;
+  if (!stride_xyz) return CONV3P_ERR_INVALID_ARGUMENT;
+  conv3p_geom_t g = make_geom(B, N, stride_xyz, voxel_size, pair_capacity);
+  st = check_geom(&g);
+  if (st) return st;
+  const size_t pb = conv3p_plan_bytes(&g);
+  if (!workspace || workspace_bytes < conv3p_op_workspace_bytes(&g, Cin, Cout))
+    return CONV3P_ERR_BUFFER_TOO_SMALL;
+  st = conv3p_plan_build_f32(&g, points, workspace, pb, stream);
+  if (st) return st;
+  st = conv3p_plan_build_backward(&g, points, workspace, pb, stream);
+  if (st) return st;
+  return conv3p_backward_f32(&g, workspace, grad_output, input, filter, Cin, Cout, grad_input,
+                             grad_filter, static_cast<char*>(workspace) + pb, workspace_bytes - pb,
+                             stream);
+}
+
+// ---- host-buffer calls -----------------------------------------------------------------------------
+
+static size_t host_io_bytes(const conv3p_geom_t* g, int Cin, int Cout) {
+  const size_t pts = (size_t)g->B * g->N;
+  const size_t nW = (size_t)C3P_NCELL * Cin * Cout;
+  // points, input, filter, out/grad_out, grad_input, grad_filter
+  return align_up(pts * 3 * 4) + align_up(pts * Cin * 4) + align_up(nW * 4) + align_up(pts * Cout * 4) +
+         align_up(pts * Cin * 4) + align_up(nW * 4);
+}
+
+size_t conv3p_host_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
+  size_t w = conv3p_op_workspace_bytes(geom, Cin, Cout);
+  if (!w) return 0;
+  return w + host_io_bytes(geom, Cin, Cout);
+}
+
+struct HostIO {
+  float *points, *input, *filter, *outg, *grad_input, *grad_filter;
+  char* op_ws;
+  size_t op_ws_bytes;
+};
+
+static HostIO carve(const conv3p_geom_t* g, int Cin, int Cout, void* ws, size_t ws_bytes) {
+  const size_t pts = (size_t)g->B * g->N;
+  const size_t nW = (size_t)C3P_NCELL * Cin * Cout;
+  char* p = static_cast<char*>(ws);
+  HostIO io;
+  io.points = reinterpret_cast<float*>(p); p += align_up(pts * 3 * 4);
+  io.input = reinterpret_cast<float*>(p); p += align_up(pts * Cin * 4);
+  io.filter = reinterpret_cast<float*>(p); p += align_up(nW * 4);
+  io.outg = reinterpret_cast<float*>(p); p += align_up(pts * Cout * 4);
+  io.grad_input = reinterpret_cast<float*>(p); p += align_up(pts * Cin * 4);
+  io.grad_filter = reinterpret_cast<float*>(p); p += align_up(nW * 4);
+  io.op_ws = p;
+  io.op_ws_bytes = ws_bytes - (size_t)(p - static_cast<char*>(ws));
+  return io;
+}
+
+int conv3p_host_forward_f32(const float* h_points, const float* h_input, const float* h_filter,
+                            const int stride_xyz[3], float voxel_size, int B, int N, int Cin,
+                            int Cout, long long pair_capacity, float* h_output, void* workspace,
+                            size_t workspace_bytes, conv3p_stream_t stream) {
+  if (!stride_xyz) return CONV3P_ERR_INVALID_ARGUMENT;
+  conv3p_geom_t g = make_geom(B, N, stride_xyz, voxel_size, pair_capacity);
+  int st = check_geom(&g);
+  if (st) return st;
+  st = check_channels(Cin, Cout);
+  if (st) return st;
+  if (!workspace || workspace_bytes < conv3p_host_workspace_bytes(&g, Cin, Cout))
+    return CONV3P_ERR_BUFFER_TOO_SMALL;
+  const size_t pts = (size_t)B * N, nW = (size_t)C3P_NCELL * Cin * Cout;
+  HostIO io = carve(&g, Cin, Cout, workspace, workspace_bytes);
+  C3P_CUDA(cudaMemcpyAsync(io.points, h_points, pts * 3 * 4, cudaMemcpyHostToDevice, stream));
+  C3P_CUDA(cudaMemcpyAsync(io.input, h_input, pts * Cin * 4, cudaMemcpyHostToDevice, stream));
+  C3P_CUDA(cudaMemcpyAsync(io.filter, h_filter, nW * 4, cudaMemcpyHostToDevice, stream));
+  const int fd[3] = {3, 3, 3};
+  st = conv3p_op_forward_f32(io.points, io.input, io.filter, fd, stride_xyz, voxel_size, B, N, Cin,
+                             Cout, pair_capacity, io.outg, io.op_ws, io.op_ws_bytes, stream);
+  if (st) return st;
+  C3P_CUDA(cudaMemcpyAsync(h_output, io.outg, pts * Cout * 4, cudaMemcpyDeviceToHost, stream));
+  C3P_CUDA(cudaStreamSynchronize(stream));
+  conv3p_plan_stats_t stats;
+  st = conv3p_plan_stats(&g, io.op_ws, &stats, stream);
+  if (st) return st;
+  return stats.overflow ? CONV3P_ERR_PAIR_OVERFLOW : CONV3P_OK;
+}
+
+int conv3p_host_backward_f32(const float* h_grad_output, const float* h_points,
+                             const float* h_input, const float* h_filter, const int stride_xyz[3],
+                             float voxel_size, int B, int N, int Cin, int Cout,
+                             long long pair_capacity, float* h_grad_input, float* h_grad_filter,
+                             void* workspace, size_t workspace_bytes, conv3p_stream_t stream) {
+  if (!stride_xyz) return CONV3P_ERR_INVALID_ARGUMENT;
+  conv3p_geom_t g = make_geom(B, N, stride_xyz, voxel_size, pair_capacity);
+  int st = check_geom(&g);
+  if (st) return st;
+  st = check_channels(Cin, Cout);
+  if (st) return st;
+  if (!workspace || workspace_bytes < conv3p_host_workspace_bytes(&g, Cin, Cout))
+    return CONV3P_ERR_BUFFER_TOO_SMALL;
+  const size_t pts = (size_t)B * N, nW = (size_t)C3P_NCELL * Cin * Cout;
+  HostIO io = carve(&g, Cin, Cout, workspace, workspace_bytes);
+  C3P_CUDA(cudaMemcpyAsync(io.points, h_points, pts * 3 * 4, cudaMemcpyHostToDevice, stream));
+  C3P_CUDA(cudaMemcpyAsync(io.input, h_input, pts * Cin * 4, cudaMemcpyHostToDevice, stream));
+  C3P_CUDA(cudaMemcpyAsync(io.filter, h_filter, nW * 4, cudaMemcpyHostToDevice, stream));
+  C3P_CUDA(cudaMemcpyAsync(io.outg, h_grad_output, pts * Cout * 4, cudaMemcpyHostToDevice, stream));
+  const int fd[3] = {3, 3, 3};
+  st = conv3p_op_backward_f32(io.outg, io.points, io.input, io.filter, fd, stride_xyz, voxel_size, B,
+                              N, Cin, Cout, pair_capacity, h_grad_input ? io.grad_input : nullptr,
+                              h_grad_filter ? io.grad_filter : nullptr, io.op_ws, io.op_ws_bytes,
+                              stream);
+  if (st) return st;
+  if (h_grad_input)
+    C3P_CUDA(cudaMemcpyAsync(h_grad_input, io.grad_input, pts * Cin * 4, cudaMemcpyDeviceToHost, stream));
+  if (h_grad_filter)
+    C3P_CUDA(cudaMemcpyAsync(h_grad_filter, io.grad_filter, nW * 4, cudaMemcpyDeviceToHost, stream));
+  C3P_CUDA(cudaStreamSynchronize(stream));
+  conv3p_plan_stats_t stats;
+  st = conv3p_plan_stats(&g, io.op_ws, &stats, stream);
+  if (st) return st;
+  return stats.overflow ? CONV3P_ERR_PAIR_OVERFLOW : CONV3P_OK;
+}
+
+}  // extern "C"

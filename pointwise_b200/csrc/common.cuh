@@ -1,0 +1,115 @@
+// common.cuh -- shared declarations of libconv3p_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/conv3p_b200.h"
+
+#define C3P_NCELL 27
+#define C3P_FULL_MASK 0xffffffffu
+
+// Header slots (int64 each) at plan_layout.header.
+enum { H_CURSOR = 0, H_OVERFLOW = 1, H_BWD_PAIRS = 2, H_HAS_BWD = 3, H_SLOTS = 16 };
+
+struct PlanView {
+  long long* header;
+  float* cloud_meta;   // [B][8]
+  uint32_t* sorted_key;
+  float4* sorted_xyzi;
+  int* count_table;
+  long long* pair_begin;
+  int* pair_len;
+  int* pair_row;
+  int* bwd_count;
+  int* bwd_row;
+  float* bwd_weight;
+  uint32_t* sort_tmp;
+};
+
+namespace c3p {
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+int compute_layout(const conv3p_geom_t* g, conv3p_plan_layout_t* L);
+int make_view(const conv3p_geom_t* g, const void* plan, size_t plan_bytes, PlanView* v);
+int check_geom(const conv3p_geom_t* g);
+
+int cuda_fail(cudaError_t e, const char* what);  // records the text, returns CONV3P_ERR_CUDA
+void count_launch(int n = 1);
+int engine();
+
+// stages (each enqueues kernels on `stream` and returns a status)
+int launch_cloud_sort(const conv3p_geom_t* g, const float* points, const PlanView& v,
+                      cudaStream_t stream);
+int launch_neighbor_search(const conv3p_geom_t* g, const PlanView& v, cudaStream_t stream);
+int launch_backward_lists(const conv3p_geom_t* g, const float* points, const PlanView& v,
+                          cudaStream_t stream);
+int launch_forward_simt(const conv3p_geom_t* g, const PlanView& v, const float* input,
+                        const float* filter, int Cin, int Cout, float* output, cudaStream_t stream);
+int launch_backward_input_simt(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
+                               const float* filter, int Cin, int Cout, float* grad_input,
+                               cudaStream_t stream);
+int launch_backward_filter_simt(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
+                                const float* input, int Cin, int Cout, float* grad_filter,
+                                void* scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t backward_filter_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout);
+
+}  // namespace c3p
+
+#define C3P_CUDA(expr)                                        \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return c3p::cuda_fail(_e, #expr);  \
+  } while (0)
+
+#define C3P_LAUNCH_CHECK(name)                                   \
+  do {                                                           \
+    cudaError_t _e = cudaGetLastError();                         \
+    if (_e != cudaSuccess) return c3p::cuda_fail(_e, name);      \
+    c3p::count_launch();                                         \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Device helpers: the reference's exact neighbour predicate (tf_conv3p_atrous.cpp:235-290), kept in
+// one place so the search, the backward re-binning and the tests of both agree bit for bit.
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace c3p {
+
+// Box bound: formed in double, rounded to float on assignment -- tf_conv3p_atrous.cpp:240-245
+// (`T xmin = x - filter_full_x * 0.5 * voxel_size;`, int*double*float).  full*0.5*voxel is exact in
+// double (<= 29 significant bits), so FMA contraction cannot change the result.
+__device__ __forceinline__ float box_lo(float centre, int full, float voxel) {
+  return __double2float_rn((double)centre - ((double)full * 0.5) * (double)voxel);
+}
+__device__ __forceinline__ float box_hi(float centre, int full, float voxel) {
+  return __double2float_rn((double)centre + ((double)full * 0.5) * (double)voxel);
+}
+
+// Tap (0..2) of coordinate v in a box starting at lo, or -1 for a dilation hole.  fp32 subtract,
+// IEEE fp32 divide (never a reciprocal multiply, never fast-math), truncation, clamp, hole test --
+// tf_conv3p_atrous.cpp:280-288.  Negative voxel indices (only reachable in the backward re-binning,
+// where the reference would index out of bounds) are reported as holes.
+__device__ __forceinline__ int tap_of(float v, float lo, float voxel, int full, int stride) {
+  int c = __float2int_rz(__fdiv_rn(__fsub_rn(v, lo), voxel));
+  c = min(c, full - 1);
+  if (c < 0) return -1;
+  int t = c / stride;
+  return (t * stride == c) ? t : -1;
+}
+
+// Uniform-grid coordinate of v: (int)((v - vmin) / cell) -- tf_conv3p_atrous.cpp:192-194.  Monotone
+// non-decreasing in v, which is all the candidate windows rely on.
+__device__ __forceinline__ int grid_coord(float v, float vmin, float cell, int dim) {
+  int c = __float2int_rz(__fdiv_rn(__fsub_rn(v, vmin), cell));
+  return max(0, min(c, dim - 1));
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+}  // namespace c3p
+#endif

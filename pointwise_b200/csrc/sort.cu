@@ -1,0 +1,176 @@
+// sort.cu -- stage 1 of the neighbour plan: per-cloud bounding box, voxel keys and a stable LSD
+// radix sort of (key, point index), one CTA per cloud, digit histograms and warp-rank tables staged
+// in shared memory.  Replaces the reference's host-side counting sort (Grid::Grid,
+// tf_conv3p_atrous.cpp:157-227) and the O(N^2) sweeps of its GPU op (tf_conv3p_atrous.cu:252-327).
+//
+// The grid is the reference's: cell size = voxel size, cell = (int)((x - vmin) / voxel) per axis,
+// dims = (int)((vmax - vmin) / voxel) + 2.  Any monotone cell function would do -- the search applies
+// the exact predicate to a superset of candidates -- so dims are clamped to 1024 per axis (a 30-bit
+// key); clouds wider than 1023 voxels merely share their last cell.
+#include "common.cuh"
+
+namespace c3p {
+
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int MAX_DIM = 1024;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_cloud_sort(const float* __restrict__ points, int N, float voxel, float* __restrict__ cloud_meta,
+             uint32_t* __restrict__ sorted_key, float4* __restrict__ sorted_xyzi,
+             uint32_t* __restrict__ tmp) {
+  __shared__ float red[6][SORT_WARPS];
+  __shared__ float box[6];
+  __shared__ uint32_t base[256];
+  __shared__ uint32_t wsum[8];
+  __shared__ uint16_t wcount[SORT_WARPS][256];
+  __shared__ uint16_t wpre[SORT_WARPS][256];
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* P = points + (size_t)b * N * 3;
+  if (N == 0) return;
+
+  // ---- bounding box (tf_conv3p_atrous.cpp:163-177: starts at +-1e6, std::min / std::max) --------
+  float mn[3] = {1e6f, 1e6f, 1e6f}, mx[3] = {-1e6f, -1e6f, -1e6f};
+  for (int i = tid; i < N; i += SORT_THREADS) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float v = P[3 * i + a];
+      mn[a] = v < mn[a] ? v : mn[a];
+      mx[a] = mx[a] < v ? v : mx[a];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    for (int o = 16; o > 0; o >>= 1) {
+      float u = __shfl_xor_sync(C3P_FULL_MASK, mn[a], o);
+      float w = __shfl_xor_sync(C3P_FULL_MASK, mx[a], o);
+      mn[a] = u < mn[a] ? u : mn[a];
+      mx[a] = mx[a] < w ? w : mx[a];
+    }
+    if (lane == 0) {
+      red[a][warp] = mn[a];
+      red[3 + a][warp] = mx[a];
+    }
+  }
+  __syncthreads();
+  if (tid < 6) {
+    float r = red[tid][0];
+    for (int w = 1; w < SORT_WARPS; ++w) {
+      float u = red[tid][w];
+      r = (tid < 3) ? (u < r ? u : r) : (r < u ? u : r);
+    }
+    box[tid] = r;
+  }
+  __syncthreads();
+  const float vminx = box[0], vminy = box[1], vminz = box[2];
+  int dim[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {  // :179-181
+    int d = __float2int_rz(__fdiv_rn(__fsub_rn(box[3 + a], box[a]), voxel)) + 2;
+    dim[a] = max(1, min(d, MAX_DIM));
+  }
+  const uint32_t cells = (uint32_t)dim[0] * dim[1] * dim[2];
+  const int nbits = cells > 1 ? 32 - __clz(cells - 1) : 0;
+  if (tid == 0) {
+    float* m = cloud_meta + 8 * b;
+    m[0] = vminx; m[1] = vminy; m[2] = vminz; m[3] = voxel;
+    m[4] = __int_as_float(dim[0]); m[5] = __int_as_float(dim[1]); m[6] = __int_as_float(dim[2]);
+    m[7] = __int_as_float(nbits);
+  }
+
+  // ---- voxel keys ---------------------------------------------------------------------------------
+  uint32_t* kin = tmp + (size_t)b * 4 * N;
+  uint32_t* iin = kin + N;
+  uint32_t* kout = kin + 2 * (size_t)N;
+  uint32_t* iout = kin + 3 * (size_t)N;
+  for (int i = tid; i < N; i += SORT_THREADS) {
+    int cx = grid_coord(P[3 * i + 0], vminx, voxel, dim[0]);
+    int cy = grid_coord(P[3 * i + 1], vminy, voxel, dim[1]);
+    int cz = grid_coord(P[3 * i + 2], vminz, voxel, dim[2]);
+    kin[i] = (uint32_t)((cz * dim[1] + cy) * dim[0] + cx);
+    iin[i] = (uint32_t)i;
+  }
+  for (int e = tid; e < SORT_WARPS * 256; e += SORT_THREADS) (&wcount[0][0])[e] = 0;
+  __syncthreads();
+
+  // ---- stable LSD radix sort, 8 bits per pass -----------------------------------------------------
+  for (int shift = 0; shift < nbits; shift += 8) {
+    if (tid < 256) base[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += SORT_THREADS) atomicAdd(&base[(kin[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    uint32_t h = 0, inc = 0;
+    if (tid < 256) {  // exclusive scan of the 256 digit counts
+      h = base[tid];
+      inc = h;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t u = __shfl_up_sync(C3P_FULL_MASK, inc, o);
+        if (lane >= o) inc += u;
+      }
+      if (lane == 31) wsum[warp] = inc;
+    }
+    __syncthreads();
+    if (tid < 256) {
+      uint32_t off = 0;
+      for (int w = 0; w < warp; ++w) off += wsum[w];
+      base[tid] = off + inc - h;
+    }
+    __syncthreads();
+
+    for (int c0 = 0; c0 < N; c0 += SORT_THREADS) {
+      const int i = c0 + tid;
+      const bool valid = i < N;
+      uint32_t key = 0, idx = 0, d = 0xffffffffu;
+      if (valid) {
+        key = kin[i];
+        idx = iin[i];
+        d = (key >> shift) & 255u;
+      }
+      const unsigned peers = __match_any_sync(C3P_FULL_MASK, d);
+      const int rank = __popc(peers & lanemask_lt());
+      if (valid && rank == 0) wcount[warp][d] = (uint16_t)__popc(peers);
+      __syncthreads();
+      uint32_t run = 0;
+      if (tid < 256) {
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+          wpre[w][tid] = (uint16_t)run;
+          run += wcount[w][tid];
+        }
+      }
+      __syncthreads();
+      if (valid) {
+        uint32_t pos = base[d] + wpre[warp][d] + rank;
+        kout[pos] = key;
+        iout[pos] = idx;
+        if (rank == 0) wcount[warp][d] = 0;  // leave the table clean for the next chunk
+      }
+      __syncthreads();
+      if (tid < 256) base[tid] += run;
+    }
+    __syncthreads();
+    uint32_t* t0 = kin; kin = kout; kout = t0;
+    uint32_t* t1 = iin; iin = iout; iout = t1;
+  }
+
+  // ---- emit sorted keys and (x, y, z, index) ------------------------------------------------------
+  for (int s = tid; s < N; s += SORT_THREADS) {
+    uint32_t idx = iin[s];
+    sorted_key[(size_t)b * N + s] = kin[s];
+    sorted_xyzi[(size_t)b * N + s] =
+        make_float4(P[3 * idx], P[3 * idx + 1], P[3 * idx + 2], __int_as_float((int)idx));
+  }
+}
+
+int launch_cloud_sort(const conv3p_geom_t* g, const float* points, const PlanView& v,
+                      cudaStream_t stream) {
+  if (g->B == 0 || g->N == 0) return CONV3P_OK;
+  k_cloud_sort<<<g->B, SORT_THREADS, 0, stream>>>(points, g->N, g->voxel_size, v.cloud_meta,
+                                                 v.sorted_key, v.sorted_xyzi, v.sort_tmp);
+  C3P_LAUNCH_CHECK("k_cloud_sort");
+  return CONV3P_OK;
+}
+
+}  // namespace c3p

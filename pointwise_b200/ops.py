@@ -1,0 +1,336 @@
+"""The Conv3p operator on PyTorch CUDA tensors -- host-side mirror of the reference's Python boundary.
+
+Reference interface being mirrored (hkust-vgd/pointwise):
+
+* ``conv3p(points_tensor, input_tensor, kernel_tensor, stride, voxel_size)``
+  -- ``pointcnn2_acsd.py:12-13``, ``scene_seg/pointcnn_scene_seg_acsd.py:11-12``
+* the registered gradient returning ``[None, input_grad, filter_grad, None, None]``
+  -- ``pointcnn2_acsd.py:15-31``
+* argument validation of the op -- ``tf_ops/conv3p/tf_conv3p_atrous.cpp:410-444, 583-585``
+  (same conditions and messages, raised as ``ValueError``).
+
+PyTorch is plumbing here (device memory, the current stream, autograd bookkeeping); all compute is
+hand-written sm_100a CUDA behind the C ABI of ``include/conv3p_b200.h``.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+NCELL = 27
+
+
+# --------------------------------------------------------------------------------------------------
+# argument handling
+# --------------------------------------------------------------------------------------------------
+def _host_list(x, what: str):
+    """stride / voxel_size may be a python scalar, a sequence, a numpy array or a tensor.  A CUDA
+    tensor forces one device->host read (the reference's GPU op does the same, blocking, at
+    tf_conv3p_atrous.cu:577,586); pass host values to stay asynchronous."""
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().reshape(-1).tolist()
+    if hasattr(x, "tolist"):
+        x = x.tolist()
+    if isinstance(x, (int, float)):
+        return [x]
+    try:
+        return list(x)
+    except TypeError as e:
+        raise ValueError(f"Conv3p: cannot interpret {what}={x!r}") from e
+
+
+def parse_stride(stride) -> tuple:
+    s = _host_list(stride, "stride")
+    if len(s) == 1 and not isinstance(stride, torch.Tensor) and not hasattr(stride, "shape"):
+        s = s * 3  # python scalar convenience: isotropic
+    if len(s) != 3:
+        raise ValueError("Conv3p expects stride tensor to have size 3.")  # tf_conv3p_atrous.cpp:437
+    s = tuple(int(v) for v in s)
+    if any(v < 1 for v in s):
+        raise ValueError("Conv3p expects strides >= 1")
+    return s
+
+
+def parse_voxel(voxel_size) -> float:
+    v = _host_list(voxel_size, "voxel_size")
+    if len(v) != 1:
+        raise ValueError("Conv3p expects voxel tensor to have dimension 1.")  # :443
+    v = float(v[0])
+    if not v > 0:
+        raise ValueError("Conv3p expects voxel_size > 0")
+    return v
+
+
+def _check_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"Conv3p: {name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"Conv3p: {name} must be a CUDA tensor (pointwise_b200 has no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"Conv3p: {name} must be float32 (got {t.dtype})")
+    return t.contiguous()
+
+
+def validate(points, input, kernel):
+    """Shape checks of Conv3pOp::Compute (tf_conv3p_atrous.cpp:410-430), same messages."""
+    if points.dim() != 3:
+        raise ValueError("Conv3p expects (batch_size, num_points, 3) points shape")  # :410
+    if points.shape[2] != 3:
+        raise ValueError("Conv3p expects (batch_size, num_points, 3) points shape")
+    if input.dim() != 3 or input.shape[0] != points.shape[0]:
+        raise ValueError("Conv3p expects points and input tensor to have the same batch size")  # :417
+    if input.shape[1] != points.shape[1]:
+        raise ValueError("Conv3p expects points and input tensor to have the same number of points")  # :418
+    if kernel.dim() != 5:
+        raise ValueError("Conv3p expects a [fz, fy, fx, in_channels, out_channels] filter")
+    if kernel.shape[3] != input.shape[2]:
+        raise ValueError("Conv3p expects filter channels to be matched with input channels")  # :430
+    if tuple(kernel.shape[:3]) != (3, 3, 3):
+        raise NotImplementedError("conv3p_b200 supports 3x3x3 filters only (all reference models)")
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+# --------------------------------------------------------------------------------------------------
+# neighbour plan
+# --------------------------------------------------------------------------------------------------
+_capacity_hint: dict = {}
+
+
+class NeighborPlan:
+    """Voxel-sorted neighbour structure of one batch of clouds for one (stride, voxel_size).
+
+    Holds the count table ``[B,N,27]`` (bit-identical to the reference's ``neighbor_count`` table,
+    tf_conv3p_atrous.cpp:369-379), the cell-grouped forward lists and, on demand, the backward lists.
+    A plan depends on ``points`` only, so it can be shared by every layer that uses the same stride and
+    by the forward and backward pass (the reference rebuilds its grid twice per layer per step,
+    tf_conv3p_atrous.cpp:463, 629).
+
+    ``capacity`` bounds the total number of (point, neighbour) pairs.  ``None`` sizes it
+    automatically: a remembered estimate is tried first and verified with one 64-byte device->host
+    read (``check=True``); with ``check=False`` nothing is read back and an overflow poisons the
+    affected outputs with NaN instead of raising.
+    """
+
+    def __init__(self, points: torch.Tensor, stride, voxel_size, capacity: Optional[int] = None,
+                 check: bool = True):
+        points = _check_cuda_f32(points, "points")
+        if points.dim() != 3 or points.shape[2] != 3:
+            raise ValueError("Conv3p expects (batch_size, num_points, 3) points shape")
+        self.points = points
+        self.stride = parse_stride(stride)
+        self.voxel_size = parse_voxel(voxel_size)
+        self.B, self.N = int(points.shape[0]), int(points.shape[1])
+        self.device = points.device
+        self.has_backward = False
+        self.stats = None
+        L = _lib.lib()
+        key = (self.B, self.N, self.stride, self.voxel_size)
+        pts = self.B * self.N
+        cap = int(capacity) if capacity is not None else _capacity_hint.get(key, max(1024, 48 * pts))
+        while True:
+            self.capacity = cap
+            self.geom = _lib.make_geom(self.B, self.N, self.stride, self.voxel_size, cap)
+            nbytes = L.conv3p_plan_bytes(self.geom)
+            if nbytes == 0:
+                raise ValueError("Conv3p: invalid geometry")
+            self.buffer = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(L.conv3p_plan_build_f32(self.geom, _ptr(points), _ptr(self.buffer), nbytes,
+                                                   _stream_ptr(self.device)))
+            if not check:
+                break
+            st = self.read_stats()
+            if not st.overflow:
+                break
+            if capacity is not None:
+                raise _lib.Conv3pError(_lib.ERR_PAIR_OVERFLOW,
+                                       f"pair capacity {cap} too small, {st.total_pairs} pairs needed")
+            cap = int(st.total_pairs * 1.125) + 1024
+        if capacity is None and check:
+            # grow-only estimate for the next batch of this shape
+            want = int(self.stats.total_pairs * 1.25) + 1024
+            _capacity_hint[key] = max(_capacity_hint.get(key, 0), want)
+        lay = _lib.PlanLayout()
+        _lib.check(L.conv3p_plan_layout(self.geom, lay))
+        self.layout = lay
+
+    # ---- stats / views -------------------------------------------------------------------------
+    def read_stats(self):
+        """Counters of the plan (synchronises the current stream)."""
+        st = _lib.PlanStats()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().conv3p_plan_stats(self.geom, _ptr(self.buffer), st,
+                                                    _stream_ptr(self.device)))
+        self.stats = st
+        return st
+
+    def _view(self, offset: int, count: int, dtype: torch.dtype) -> torch.Tensor:
+        nbytes = count * torch.empty((), dtype=dtype).element_size()
+        return self.buffer[offset:offset + nbytes].view(dtype)
+
+    @property
+    def count_table(self) -> torch.Tensor:
+        return self._view(self.layout.count_table, self.B * self.N * NCELL, torch.int32) \
+            .view(self.B, self.N, NCELL)
+
+    @property
+    def backward_count_table(self) -> torch.Tensor:
+        return self._view(self.layout.bwd_count, self.B * self.N * NCELL, torch.int32) \
+            .view(self.B, self.N, NCELL)
+
+    @property
+    def pair_begin(self) -> torch.Tensor:
+        return self._view(self.layout.pair_begin, self.B * self.N, torch.int64).view(self.B, self.N)
+
+    @property
+    def pair_len(self) -> torch.Tensor:
+        return self._view(self.layout.pair_len, self.B * self.N, torch.int32).view(self.B, self.N)
+
+    @property
+    def pair_row(self) -> torch.Tensor:
+        return self._view(self.layout.pair_row, self.capacity, torch.int32)
+
+    @property
+    def backward_row(self) -> torch.Tensor:
+        return self._view(self.layout.bwd_row, self.capacity, torch.int32)
+
+    @property
+    def backward_weight(self) -> torch.Tensor:
+        return self._view(self.layout.bwd_weight, self.capacity, torch.float32)
+
+    @property
+    def sorted_xyzi(self) -> torch.Tensor:
+        return self._view(self.layout.sorted_xyzi, self.B * self.N * 4, torch.float32) \
+            .view(self.B, self.N, 4)
+
+    @property
+    def sorted_key(self) -> torch.Tensor:
+        return self._view(self.layout.sorted_key, self.B * self.N, torch.int32).view(self.B, self.N)
+
+    # ---- backward lists ----------------------------------------------------------------------------
+    def ensure_backward(self) -> "NeighborPlan":
+        if not self.has_backward:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().conv3p_plan_build_backward(
+                    self.geom, _ptr(self.points), _ptr(self.buffer), self.buffer.numel(),
+                    _stream_ptr(self.device)))
+            self.has_backward = True
+        return self
+
+    def matches(self, points: torch.Tensor, stride: tuple, voxel: float) -> bool:
+        return (points.data_ptr() == self.points.data_ptr() and tuple(points.shape) == (self.B, self.N, 3)
+                and stride == self.stride and voxel == self.voxel_size)
+
+
+# --------------------------------------------------------------------------------------------------
+# forward / backward on a plan
+# --------------------------------------------------------------------------------------------------
+def conv3p_forward(plan: NeighborPlan, input: torch.Tensor, kernel: torch.Tensor) -> torch.Tensor:
+    input = _check_cuda_f32(input, "input")
+    kernel = _check_cuda_f32(kernel, "kernel")
+    Cin, Cout = int(kernel.shape[3]), int(kernel.shape[4])
+    out = torch.empty((plan.B, plan.N, Cout), dtype=torch.float32, device=plan.device)
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.lib().conv3p_forward_f32(plan.geom, _ptr(plan.buffer), _ptr(input), _ptr(kernel),
+                                                 Cin, Cout, _ptr(out), None, 0,
+                                                 _stream_ptr(plan.device)))
+    return out
+
+
+def conv3p_backward(plan: NeighborPlan, grad_output: torch.Tensor, input: torch.Tensor,
+                    kernel: torch.Tensor, need_input_grad: bool = True,
+                    need_filter_grad: bool = True):
+    grad_output = _check_cuda_f32(grad_output, "grad_output")
+    input = _check_cuda_f32(input, "input")
+    kernel = _check_cuda_f32(kernel, "kernel")
+    Cin, Cout = int(kernel.shape[3]), int(kernel.shape[4])
+    # shape checks of Conv3pGradOp::Compute, tf_conv3p_atrous.cpp:583-585
+    if grad_output.shape[0] != plan.B:
+        raise ValueError("backprop grad tensor has wrong size for dim 0")
+    if grad_output.shape[1] != plan.N:
+        raise ValueError("backprop grad tensor has wrong size for dim 1")
+    if grad_output.shape[2] != Cout:
+        raise ValueError("backprop grad tensor has wrong size for dim 2")
+    plan.ensure_backward()
+    L = _lib.lib()
+    gi = torch.empty((plan.B, plan.N, Cin), dtype=torch.float32, device=plan.device) \
+        if need_input_grad else None
+    gf = torch.empty_like(kernel) if need_filter_grad else None
+    scratch = None
+    nscratch = 0
+    if need_filter_grad:
+        nscratch = L.conv3p_scratch_bytes(plan.geom, Cin, Cout)
+        scratch = torch.empty(nscratch, dtype=torch.uint8, device=plan.device)
+    with torch.cuda.device(plan.device):
+        _lib.check(L.conv3p_backward_f32(plan.geom, _ptr(plan.buffer), _ptr(grad_output), _ptr(input),
+                                         _ptr(kernel), Cin, Cout, _ptr(gi), _ptr(gf), _ptr(scratch),
+                                         nscratch, _stream_ptr(plan.device)))
+    return gi, gf
+
+
+class _Conv3pFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, input, kernel, plan):
+        ctx.plan = plan
+        ctx.save_for_backward(input, kernel)
+        return conv3p_forward(plan, input, kernel)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, kernel = ctx.saved_tensors
+        gi, gf = conv3p_backward(ctx.plan, grad_output, input, kernel,
+                                 need_input_grad=ctx.needs_input_grad[1],
+                                 need_filter_grad=ctx.needs_input_grad[2])
+        # the reference returns [None, input_grad, filter_grad, None, None] (pointcnn2_acsd.py:31)
+        return None, gi, gf, None
+
+
+def conv3p(points_tensor, input_tensor, kernel_tensor, stride, voxel_size,
+           plan: Optional[NeighborPlan] = None) -> torch.Tensor:
+    """Drop-in for the reference's ``conv3p`` (pointcnn2_acsd.py:12-13): same positional signature.
+
+    points [B,N,3], input [B,N,Cin], kernel [3,3,3,Cin,Cout] (z,y,x,in,out), stride = 3 ints (x,y,z),
+    voxel_size = 1 float; returns [B,N,Cout].  Differentiable w.r.t. input and kernel only
+    (pointcnn2_acsd.py:31).  ``plan`` optionally reuses a NeighborPlan built for the same points,
+    stride and voxel size (e.g. across layers).
+    """
+    points = _check_cuda_f32(points_tensor, "points")
+    input = _check_cuda_f32(input_tensor, "input")
+    kernel = _check_cuda_f32(kernel_tensor, "kernel")
+    validate(points, input, kernel)
+    s, v = parse_stride(stride), parse_voxel(voxel_size)
+    if plan is None:
+        plan = NeighborPlan(points, s, v)
+    elif not plan.matches(points, s, v):
+        raise ValueError("Conv3p: the supplied NeighborPlan was built for different points/stride/voxel_size")
+    return _Conv3pFunction.apply(points, input, kernel, plan)
+
+
+def conv3p_grad(grad_from_next, points, input, filter, stride, voxel_size,
+                plan: Optional[NeighborPlan] = None):
+    """Mirror of the reference's ``conv3p_grad`` op (register_op.cpp:63-75):
+    -> (input_grad, filter_grad)."""
+    points = _check_cuda_f32(points, "points")
+    input = _check_cuda_f32(input, "input")
+    filter = _check_cuda_f32(filter, "filter")
+    validate(points, input, filter)
+    s, v = parse_stride(stride), parse_voxel(voxel_size)
+    if plan is None:
+        plan = NeighborPlan(points, s, v)
+    return conv3p_backward(plan, grad_from_next, input, filter)
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernels launched by the library on this thread since the last reset."""
+    return int(_lib.lib().conv3p_launch_count(1 if reset else 0))

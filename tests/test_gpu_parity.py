@@ -1,0 +1,347 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU checker on identical inputs.
+
+Bar (BASELINE.json north_star): neighbour indices BIT-EXACT; features within a stated fp32 tolerance.
+Feature tolerance used here:  |got - truth| <= ATOL + RTOL * sum|terms|  with truth and sum|terms|
+accumulated in float64 by the oracle over the reference's own pair set.  RTOL = 1e-5 is the size of
+the reference's own fp32 summation error (it adds ~K*Cin rounded terms sequentially), so "within
+tolerance" means "as close to the exact sum as the reference itself".
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close_scaled, pair_sets
+from pointwise_b200.synth import make_points, make_problem
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+ATOL = 1e-7
+V = 0.1
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_lists(plan):
+    """-> count[B,N,27], and per cloud (off, j_local, f) reconstructed from the cell-grouped lists."""
+    cnt = plan.count_table.cpu().numpy()
+    begin = plan.pair_begin.cpu().numpy()
+    length = plan.pair_len.cpu().numpy()
+    rows = plan.pair_row.cpu().numpy()
+    B, N = plan.B, plan.N
+    clouds = []
+    for b in range(B):
+        off = np.zeros(N + 1, np.int64)
+        js, fs = [], []
+        for i in range(N):
+            seg = rows[begin[b, i]:begin[b, i] + length[b, i]]
+            assert length[b, i] == cnt[b, i].sum()
+            assert ((seg >= b * N) & (seg < (b + 1) * N)).all(), "neighbour from another cloud"
+            js.append(seg - b * N)
+            fs.append(np.repeat(np.arange(27), cnt[b, i]))
+            off[i + 1] = off[i] + length[b, i]
+        clouds.append((off, np.concatenate(js) if js else np.zeros(0, np.int64),
+                       np.concatenate(fs) if fs else np.zeros(0, np.int64)))
+    return cnt, clouds
+
+
+INDEX_CASES = [
+    # B, N, stride, dist, quantise
+    (4, 1024, (1, 1, 1), "sphere", None),
+    (2, 1024, (2, 2, 2), "sphere", None),
+    (2, 1000, (3, 3, 3), "room", None),
+    (2, 777, (4, 4, 4), "room", None),
+    (2, 2048, (1, 1, 1), "room", 0.05),     # bin-edge ties: asymmetry stress
+    (2, 1024, (2, 2, 2), "cube", 0.05),
+    (1, 4096, (1, 1, 1), "room", None),
+    (2, 600, (1, 2, 3), "room", None),      # anisotropic stride
+    (1, 1, (1, 1, 1), "cube", None),        # single point
+    (3, 33, (4, 4, 4), "cube", 0.1),
+]
+
+
+@pytest.mark.parametrize("B,N,stride,dist,q", INDEX_CASES)
+def test_neighbor_indices_bit_exact(checker, B, N, stride, dist, q):
+    from pointwise_b200 import NeighborPlan
+    pts = make_points(B, N, dist, seed=3, quantise=q)
+    plan = NeighborPlan(dev(pts), stride, V)
+    cnt, clouds = gpu_lists(plan)
+    assert plan.stats.total_pairs == cnt.sum()
+    for b in range(B):
+        want_cnt = checker.neighbor_count(pts[b], stride, V)
+        assert np.array_equal(cnt[b], want_cnt), f"count table differs in cloud {b}"
+        off, j, f = checker.neighbors(pts[b], stride, V)
+        goff, gj, gf = clouds[b]
+        assert np.array_equal(off, goff)
+        for i, (a, c) in enumerate(zip(pair_sets(off, j, f, N), pair_sets(goff, gj, gf, N))):
+            assert np.array_equal(a, c), f"pair set differs at cloud {b} point {i}"
+
+
+def test_dense_neighbourhood_uses_resweep(checker):
+    """600 identical points + 400 spread ones: K = 600 per point exceeds the shared-memory stash."""
+    from pointwise_b200 import NeighborPlan
+    rng = np.random.default_rng(0)
+    pts = np.concatenate([np.full((600, 3), 0.25, np.float32),
+                          rng.uniform(-1, 1, (400, 3)).astype(np.float32)])[None]
+    plan = NeighborPlan(dev(pts), 1, V)
+    cnt, clouds = gpu_lists(plan)
+    assert np.array_equal(cnt[0], checker.neighbor_count(pts[0], 1, V))
+    off, j, f = checker.neighbors(pts[0], 1, V)
+    for a, c in zip(pair_sets(off, j, f, 1000), pair_sets(*clouds[0], 1000)):
+        assert np.array_equal(a, c)
+    assert cnt[0, :600, 13].min() >= 600
+
+
+def test_far_from_origin_and_tiny_voxel(checker):
+    from pointwise_b200 import NeighborPlan
+    pts = make_points(2, 500, "cube", seed=9) * 0.02 + np.float32(100.0)
+    for voxel, stride in [(0.001, 1), (0.003, 2)]:
+        plan = NeighborPlan(dev(pts), stride, voxel)
+        cnt = plan.count_table.cpu().numpy()
+        for b in range(2):
+            assert np.array_equal(cnt[b], checker.neighbor_count(pts[b], stride, voxel))
+
+
+def test_backward_lists_follow_reference_rule(port):
+    """Backward pair multiset == {(j, ii, f') : ii in N(j), f' not a hole, count(ii,f') > 0}."""
+    from pointwise_b200 import NeighborPlan
+    B, N, stride = 2, 1024, (1, 1, 1)
+    pts = make_points(B, N, "room", seed=5, quantise=0.05)
+    plan = NeighborPlan(dev(pts), stride, V).ensure_backward()
+    bc = plan.backward_count_table.cpu().numpy()
+    begin = plan.pair_begin.cpu().numpy()
+    brow = plan.backward_row.cpu().numpy()
+    bw = plan.backward_weight.cpu().numpy()
+    n_asym = 0
+    for b in range(B):
+        cnt = port.neighbor_count(pts[b], stride, V)
+        off, j, f = port.neighbors(pts[b], stride, V)
+        for jj in range(N):
+            want = []
+            for ii in j[off[jj]:off[jj + 1]]:
+                lo = (pts[b, ii].astype(np.float64) - 3 * 0.5 * np.float64(np.float32(V))).astype(np.float32)
+                c = np.minimum(2, ((pts[b, jj] - lo) / np.float32(V)).astype(np.int32))
+                fp = (c[2] * 3 + c[1]) * 3 + c[0]
+                if cnt[ii, fp] > 0:
+                    want.append((fp, ii, cnt[ii, fp]))
+                else:
+                    n_asym += 1
+            k = bc[b, jj].sum()
+            seg = brow[begin[b, jj]:begin[b, jj] + k] - b * N
+            wts = bw[begin[b, jj]:begin[b, jj] + k]
+            fs = np.repeat(np.arange(27), bc[b, jj])
+            got = sorted(zip(fs.tolist(), seg.tolist(), np.rint(1.0 / wts).astype(int).tolist()))
+            assert got == sorted((int(a), int(c), int(d)) for a, c, d in want), (b, jj)
+    assert plan.read_stats().backward_pairs == bc.sum()
+    assert n_asym > 0, "quantised cloud should exercise the count==0 skip"
+
+
+FEATURE_CASES = [
+    # B, N, Cin, Cout, stride, dist, quantise
+    (4, 1024, 9, 9, (1, 1, 1), "sphere", None),     # BASELINE config 1
+    (2, 1024, 3, 9, (1, 1, 1), "sphere", None),     # ModelNet40 layer 1
+    (2, 1024, 9, 9, (2, 2, 2), "sphere", None),
+    (2, 1024, 9, 9, (3, 3, 3), "room", None),
+    (2, 1024, 9, 9, (4, 4, 4), "room", None),
+    (2, 2048, 36, 13, (1, 1, 1), "room", None),     # S3DIS layer 5
+    (2, 2048, 64, 128, (1, 1, 1), "room", None),    # headline shape
+    (1, 1500, 64, 128, (1, 1, 1), "room", 0.05),    # asymmetric pairs, N not a tile multiple
+    (2, 512, 5, 7, (1, 2, 3), "cube", 0.05),
+    (1, 300, 40, 300, (1, 1, 1), "room", None),     # Cout beyond one column block
+    (1, 1, 4, 4, (1, 1, 1), "cube", None),
+]
+
+
+@pytest.mark.parametrize("B,N,Cin,Cout,stride,dist,q", FEATURE_CASES)
+def test_forward_backward_parity(port, checker, B, N, Cin, Cout, stride, dist, q):
+    from pointwise_b200 import NeighborPlan, conv3p_backward, conv3p_forward
+    pr = make_problem(B, N, Cin, Cout, dist, seed=2, quantise=q)
+    plan = NeighborPlan(dev(pr["points"]), stride, V)
+    out = conv3p_forward(plan, dev(pr["input"]), dev(pr["filter"])).cpu().numpy()
+    o32, o64, oabs = port.forward(pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
+    assert_close_scaled(out, o64, oabs, RTOL, ATOL, "forward")
+    assert_close_scaled(o32, o64, oabs, RTOL, ATOL, "oracle fp32 vs fp64 (tolerance sanity)")
+
+    gi, gf = conv3p_backward(plan, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]))
+    r = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
+    assert_close_scaled(gi.cpu().numpy(), r[2], r[3], RTOL, ATOL, "grad_input")
+    assert_close_scaled(gf.cpu().numpy(), r[4], r[5], RTOL, ATOL, "grad_filter")
+    if checker.kind == "reference" and B * N * Cin * Cout <= 2048 * 36 * 13 * 2:
+        # the reference's own object code agrees with the port it pins
+        assert np.array_equal(checker.forward(pr["points"], pr["input"], pr["filter"], stride, V), o32)
+
+
+KATS = [
+    # points (x,y,z), input, grad, stride -> out, grad_in, {cell: grad_W}     
+    ([(0, 0, 0)], [2], [1], 1, [26], [13], {13: 2}),
+    ([(0, 0, 0), (0.1, 0, 0)], [2, 3], [1, 10], 1, [68, 63], [133, 144], {12: 20, 13: 32, 14: 3}),
+    ([(0, 0, 0), (0.15, 0, 0)], [2, 3], [1, 10], 1, [68, 39], [13, 130], {13: 32}),
+    ([(0, 0, 0), (0.16, 0, 0)], [2, 3], [1, 10], 1, [26, 39], None, None),
+    ([(0, 0, 0), (0.06, 0, 0), (0.07, 0, 0)], [2, 3, 5], [1, 10, 100], 1, [82, 76, 76],
+     [1333, 722, 722], {12: 220, 13: 442, 14: 4}),
+    ([(0, 0, 0), (0.1, 0, 0), (0.2, 0, 0)], [2, 3, 5], [1, 10, 100], 2, [96, 39, 89],
+     [1213, 130, 1314], {12: 200, 13: 532, 14: 5}),
+    ([(0, 0, 0), (0.1, 0.1, 0.1)], [2, 3], [1, 10], 1, [104, 39], None, {0: 20, 13: 32, 26: 3}),
+]
+
+
+@pytest.mark.parametrize("k", range(len(KATS)))
+def test_known_answers(k):
+    from pointwise_b200 import conv3p
+    pts, inp, g, stride, out, gin, gw = KATS[k]
+    P = torch.tensor([pts], dtype=torch.float32).cuda()
+    X = torch.tensor(inp, dtype=torch.float32).view(1, -1, 1).cuda().requires_grad_()
+    W = torch.arange(27, dtype=torch.float32).view(3, 3, 3, 1, 1).cuda().requires_grad_()
+    y = conv3p(P, X, W, [stride] * 3, [0.1])
+    assert y.flatten().tolist() == [float(v) for v in out]
+    y.backward(torch.tensor(g, dtype=torch.float32).view(1, -1, 1).cuda())
+    if gin is not None:
+        assert X.grad.flatten().tolist() == [float(v) for v in gin]
+    if gw is not None:
+        want = np.zeros(27)
+        for c, v in gw.items():
+            want[c] = v
+        assert W.grad.flatten().tolist() == want.tolist()
+
+
+def test_autograd_signature_and_gradients(port):
+    from pointwise_b200 import conv3p
+    pr = make_problem(2, 512, 9, 9, "sphere", seed=4)
+    P = dev(pr["points"]).requires_grad_()
+    X = dev(pr["input"]).requires_grad_()
+    W = dev(pr["filter"]).requires_grad_()
+    stride = torch.tensor([2, 2, 2], dtype=torch.int32)      # host tensors, as tf.constant in the models
+    voxel = torch.tensor([0.1])
+    y = conv3p(P, X, W, stride, voxel)
+    assert y.shape == (2, 512, 9)
+    y.backward(dev(pr["grad_out"]))
+    assert P.grad is None                                      # no gradient to points (pointcnn2_acsd.py:31)
+    gi, gf, gi64, gia, gf64, gfa = port.backward(pr["grad_out"], pr["points"], pr["input"],
+                                                 pr["filter"], 2, V, with64=True)
+    assert_close_scaled(X.grad.cpu().numpy(), gi64, gia, RTOL, ATOL, "autograd grad_input")
+    assert_close_scaled(W.grad.cpu().numpy(), gf64, gfa, RTOL, ATOL, "autograd grad_filter")
+
+
+def test_plan_reuse_and_determinism():
+    from pointwise_b200 import NeighborPlan, conv3p_backward, conv3p_forward
+    pr = make_problem(2, 2048, 16, 16, "room", seed=6)
+    P, X, W, G = (dev(pr[k]) for k in ("points", "input", "filter", "grad_out"))
+    a = NeighborPlan(P, 1, V)
+    b = NeighborPlan(P, 1, V)
+    ya, yb = conv3p_forward(a, X, W), conv3p_forward(b, X, W)
+    assert torch.equal(ya, yb), "forward must not depend on where the lists landed in memory"
+    ga, gb = conv3p_backward(a, G, X, W), conv3p_backward(b, G, X, W)
+    assert torch.equal(ga[0], gb[0]) and torch.equal(ga[1], gb[1]), "backward must be deterministic"
+
+
+def test_reference_error_messages():
+    from pointwise_b200 import conv3p
+    P = torch.zeros(2, 8, 3).cuda()
+    X = torch.zeros(2, 8, 4).cuda()
+    W = torch.zeros(3, 3, 3, 4, 5).cuda()
+    with pytest.raises(ValueError, match="points shape"):
+        conv3p(P.view(16, 3), X, W, [1, 1, 1], [0.1])
+    with pytest.raises(ValueError, match="same batch size"):
+        conv3p(P, X[:1], W, [1, 1, 1], [0.1])
+    with pytest.raises(ValueError, match="same number of points"):
+        conv3p(P, X[:, :4], W, [1, 1, 1], [0.1])
+    with pytest.raises(ValueError, match="filter channels"):
+        conv3p(P, X, torch.zeros(3, 3, 3, 3, 5).cuda(), [1, 1, 1], [0.1])
+    with pytest.raises(ValueError, match="stride tensor to have size 3"):
+        conv3p(P, X, W, [1, 1], [0.1])
+    with pytest.raises(ValueError, match="voxel tensor to have dimension 1"):
+        conv3p(P, X, W, [1, 1, 1], [0.1, 0.2])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        conv3p(P.cpu(), X, W, [1, 1, 1], [0.1])
+
+
+def test_explicit_capacity_overflow_is_reported():
+    from pointwise_b200 import Conv3pError, NeighborPlan
+    pts = dev(make_points(1, 512, "sphere", seed=1))
+    with pytest.raises(Conv3pError, match="capacity"):
+        NeighborPlan(pts, 1, V, capacity=600)
+    # unchecked plans poison instead of raising
+    from pointwise_b200 import conv3p_forward
+    plan = NeighborPlan(pts, 1, V, capacity=600, check=False)
+    y = conv3p_forward(plan, torch.ones(1, 512, 4).cuda(), torch.ones(3, 3, 3, 4, 4).cuda())
+    assert torch.isnan(y).any() and not torch.isnan(y).all()
+
+
+def test_full_size_properties():
+    """BASELINE headline size (N=4096, 64->128): size-independent properties instead of the oracle."""
+    from pointwise_b200 import NeighborPlan, conv3p_backward, conv3p_forward
+    B, N, Cin, Cout = 16, 4096, 64, 128
+    pr = make_problem(B, N, Cin, Cout, "room", seed=0)
+    P, X, W, G = (dev(pr[k]) for k in ("points", "input", "filter", "grad_out"))
+    plan = NeighborPlan(P, 1, V)
+    cnt = plan.count_table
+    assert int(cnt.sum()) == plan.stats.total_pairs
+    assert int(cnt[:, :, 13].min()) >= 1, "every point is its own neighbour in the centre cell"
+    # mirror symmetry of the counts: pairs in cell f of i <-> cell 26-f of j (up to edge rounding)
+    per_cell = cnt.sum(dim=(0, 1)).double()
+    assert torch.allclose(per_cell, per_cell.flip(0), rtol=1e-3)
+    # linearity in the input and in the filter
+    y1 = conv3p_forward(plan, X, W)
+    X2 = torch.randn_like(X)
+    y2 = conv3p_forward(plan, X2, W)
+    y12 = conv3p_forward(plan, 0.5 * X + 2.0 * X2, W)
+    scale = (0.5 * y1).abs() + (2.0 * y2).abs() + 1e-3
+    assert ((y12 - (0.5 * y1 + 2.0 * y2)).abs() / scale).max() < 1e-4
+    # a constant input and a filter that is constant over (k) reproduces sum_f W[f] over non-empty cells
+    ones = torch.ones_like(X)
+    Wc = torch.randn(27, 1, Cout, device="cuda").expand(27, Cin, Cout).contiguous().view(3, 3, 3, Cin, Cout)
+    yc = conv3p_forward(plan, ones, Wc)
+    want = torch.einsum("bnf,fc->bnc", (cnt > 0).float(), Wc.view(27, Cin, Cout).sum(1))
+    assert torch.allclose(yc, want, rtol=1e-4, atol=1e-3)
+    # adjoint identities (exact up to the rare non-symmetric edge pairs of continuous data)
+    gi, gf = conv3p_backward(plan, G, X, W)
+    lhs = (G.double() * y1.double()).sum()
+    assert abs(lhs - (gi.double() * X.double()).sum()) <= 1e-3 * abs(lhs) + 1.0
+    assert abs(lhs - (gf.double() * W.double()).sum()) <= 1e-3 * abs(lhs) + 1.0
+
+
+def test_c_abi_one_shot_and_host_calls(port):
+    """The reference-facing C entry points: device one-shot calls and host-buffer calls."""
+    import ctypes as C
+    from pointwise_b200 import _lib
+    L = _lib.lib()
+    B, N, Cin, Cout, stride = 2, 700, 9, 13, (2, 2, 2)
+    pr = make_problem(B, N, Cin, Cout, "room", seed=8)
+    cap = 64 * B * N
+    g = _lib.make_geom(B, N, stride, V, cap)
+    i3 = (C.c_int * 3)
+    # host-buffer calls
+    ws = torch.empty(L.conv3p_host_workspace_bytes(g, Cin, Cout), dtype=torch.uint8, device="cuda")
+    out = np.zeros((B, N, Cout), np.float32)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    _lib.check(L.conv3p_host_forward_f32(p(pr["points"]), p(pr["input"]), p(pr["filter"]), i3(*stride),
+                                         V, B, N, Cin, Cout, cap, p(out), C.c_void_p(ws.data_ptr()),
+                                         ws.numel(), None))
+    o32, o64, oabs = port.forward(pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
+    assert_close_scaled(out, o64, oabs, RTOL, ATOL, "host forward")
+    gi = np.zeros((B, N, Cin), np.float32)
+    gf = np.zeros((3, 3, 3, Cin, Cout), np.float32)
+    _lib.check(L.conv3p_host_backward_f32(p(pr["grad_out"]), p(pr["points"]), p(pr["input"]),
+                                          p(pr["filter"]), i3(*stride), V, B, N, Cin, Cout, cap, p(gi),
+                                          p(gf), C.c_void_p(ws.data_ptr()), ws.numel(), None))
+    r = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
+    assert_close_scaled(gi, r[2], r[3], RTOL, ATOL, "host grad_input")
+    assert_close_scaled(gf, r[4], r[5], RTOL, ATOL, "host grad_filter")
+    # capacity too small -> status, not a crash
+    st = L.conv3p_host_forward_f32(p(pr["points"]), p(pr["input"]), p(pr["filter"]), i3(*stride), V, B,
+                                   N, Cin, Cout, 100, p(out), C.c_void_p(ws.data_ptr()), ws.numel(), None)
+    assert st == _lib.ERR_PAIR_OVERFLOW
+    # unsupported filter size -> status
+    P, X, W = dev(pr["points"]), dev(pr["input"]), dev(pr["filter"])
+    Y = torch.empty(B, N, Cout, device="cuda")
+    ws2 = torch.empty(L.conv3p_op_workspace_bytes(g, Cin, Cout), dtype=torch.uint8, device="cuda")
+    st = L.conv3p_op_forward_f32(P.data_ptr(), X.data_ptr(), W.data_ptr(), i3(5, 3, 3), i3(*stride), V, B,
+                                 N, Cin, Cout, cap, Y.data_ptr(), ws2.data_ptr(), ws2.numel(), None)
+    assert st == _lib.ERR_UNSUPPORTED
+    _lib.check(L.conv3p_op_forward_f32(P.data_ptr(), X.data_ptr(), W.data_ptr(), i3(3, 3, 3), i3(*stride),
+                                       V, B, N, Cin, Cout, cap, Y.data_ptr(), ws2.data_ptr(),
+                                       ws2.numel(), None))
+    torch.cuda.synchronize()
+    assert_close_scaled(Y.cpu().numpy(), o64, oabs, RTOL, ATOL, "one-shot forward")

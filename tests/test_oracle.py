@@ -1,0 +1,118 @@
+"""CPU tests of the checkers themselves: the C port against the golden vectors (generated from the
+reference's own object code, tests/golden/make_golden.py) and, where oracle/_ref is present, against
+the reference directly."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import pair_sets
+from pointwise_b200.synth import make_problem
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+V = 0.1
+
+
+def test_golden_fixtures_present():
+    assert len(GOLDEN) >= 12
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_port_matches_golden(port, path):
+    d = np.load(path)
+    s, v = d["stride"], float(d["voxel"])
+    out = port.forward(d["points"], d["input"], d["filter"], s, v)
+    assert np.array_equal(out, d["output"]), "forward must be bit-exact (same order of operations)"
+    gi, gf = port.backward(d["grad_out"], d["points"], d["input"], d["filter"], s, v)
+    assert np.array_equal(gi, d["grad_input"])
+    if d["points"].shape[0] == 1:
+        assert np.array_equal(gf, d["grad_filter"])       # one cloud: same summation order
+    else:
+        np.testing.assert_allclose(gf, d["grad_filter"], rtol=1e-5, atol=1e-5)
+    for b in range(d["points"].shape[0]):
+        assert np.array_equal(port.neighbor_count(d["points"][b], s, v), d["count_table"][b])
+
+
+def test_known_answers_by_hand(port):
+    """KAT2 of SURVEY section 8c, derivable by hand: x={0,0.1}, in={2,3}, W[f]=f."""
+    P = np.zeros((1, 2, 3), np.float32)
+    P[0, 1, 0] = 0.1
+    X = np.array([[[2], [3]]], np.float32)
+    W = np.arange(27, dtype=np.float32).reshape(3, 3, 3, 1, 1)
+    assert port.forward(P, X, W, 1, V).ravel().tolist() == [68.0, 63.0]
+    gi, gf = port.backward(np.array([[[1], [10]]], np.float32), P, X, W, 1, V)
+    assert gi.ravel().tolist() == [133.0, 144.0]
+    assert gf.ravel()[[12, 13, 14]].tolist() == [20.0, 32.0, 3.0]
+
+
+@pytest.mark.parametrize("B,N,Ci,Co,stride,dist,q", [
+    (3, 512, 9, 9, (1, 1, 1), "sphere", None),
+    (2, 700, 3, 9, (2, 2, 2), "room", None),
+    (2, 400, 5, 4, (4, 4, 4), "room", 0.05),
+    (1, 600, 4, 4, (1, 3, 2), "cube", 0.05),
+])
+def test_port_matches_reference_object_code(port, B, N, Ci, Co, stride, dist, q):
+    import oracle
+    if not oracle.Ref.available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    R = oracle.ref()
+    pr = make_problem(B, N, Ci, Co, dist, seed=21, quantise=q)
+    assert np.array_equal(port.forward(pr["points"], pr["input"], pr["filter"], stride, V),
+                          R.forward(pr["points"], pr["input"], pr["filter"], stride, V))
+    gi, gf = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, V)
+    ri, rf = R.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, V)
+    assert np.array_equal(gi, ri)
+    np.testing.assert_allclose(gf, rf, rtol=1e-4, atol=1e-4)   # reduction order differs (OpenMP copies)
+    for b in range(B):
+        assert np.array_equal(port.neighbor_count(pr["points"][b], stride, V),
+                              R.neighbor_count(pr["points"][b], stride, V))
+        a = port.neighbors(pr["points"][b], stride, V)
+        c = R.neighbors(pr["points"][b], stride, V)
+        assert all(np.array_equal(x, y) for x, y in zip(a, c)), "emission order must match too"
+
+
+def test_grid_window_never_drops_a_neighbour(port):
+    """The grid-windowed search equals the brute-force predicate (hard part 2)."""
+    for dist, q, stride in [("room", None, (1, 1, 1)), ("cube", 0.05, (2, 2, 2)), ("room", 0.05, (3, 1, 2))]:
+        pr = make_problem(1, 800, 1, 1, dist, seed=31, quantise=q)
+        assert np.array_equal(port.neighbor_count(pr["points"][0], stride, V),
+                              port.neighbor_count(pr["points"][0], stride, V, bruteforce=True))
+
+
+def test_reference_rejects_bad_shapes():
+    """The reference's own OP_REQUIRES messages (tf_conv3p_atrous.cpp:410-443) -- the Python host
+    layer raises the same texts (tests/test_host_logic.py)."""
+    import oracle
+    if not oracle.Ref.available():
+        pytest.skip("oracle/_ref not built")
+    R = oracle.ref()
+    pr = make_problem(2, 16, 3, 4, "cube", seed=1)
+    a = (pr["points"], pr["input"], pr["filter"], 1, V)
+    with pytest.raises(ValueError, match="points shape"):
+        R.forward(*a, points_rank3=False)
+    with pytest.raises(ValueError, match="same batch size"):
+        R.forward(*a, input_shape=(1, 16))
+    with pytest.raises(ValueError, match="same number of points"):
+        R.forward(*a, input_shape=(2, 8))
+    with pytest.raises(ValueError, match="filter channels"):
+        R.forward(*a, filter_cin=5)
+    with pytest.raises(ValueError, match="stride tensor to have size 3"):
+        R.forward(*a, raw_stride=[1, 1])
+    with pytest.raises(ValueError, match="voxel tensor to have dimension 1"):
+        R.forward(*a, raw_voxel=[0.1, 0.1])
+    with pytest.raises(ValueError, match="wrong size for dim 2"):
+        R.backward(pr["grad_out"], *a, grad_shape=(2, 16, 5))
+
+
+def test_asymmetric_pairs_exist_on_quantised_clouds(port):
+    """The reference's backward is not the adjoint of its forward at bin edges (KAT3): on a lattice
+    cloud <g, conv(x)> != <grad_input, x>; on continuous data the two agree."""
+    for q, expect_equal in [(None, True), (0.05, False)]:
+        pr = make_problem(1, 600, 2, 2, "cube", seed=41, quantise=q)
+        y = port.forward(pr["points"], pr["input"], pr["filter"], 1, V).astype(np.float64)
+        gi, _ = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], 1, V)
+        lhs = (pr["grad_out"] * y).sum()
+        rhs = (gi.astype(np.float64) * pr["input"]).sum()
+        close = abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+        assert close == expect_equal
