@@ -165,6 +165,13 @@ long long conv3p_launch_count(int reset);
  * supported.  Returns the previous value.  Process-wide. */
 int conv3p_set_engine(int engine);
 
+/* Per-kernel timing for benchmarks: while enabled, every kernel launch is bracketed by CUDA events
+ * on its stream.  conv3p_profile_enable(on) clears the records and returns the previous state.
+ * conv3p_profile_read writes "kernel_name launches total_ms\n" lines into buf (after the caller
+ * synchronised) and returns the number of launches recorded. */
+int conv3p_profile_enable(int on);
+long long conv3p_profile_read(char* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ EXPORTS = [
     "conv3p_op_workspace_bytes", "conv3p_op_forward_f32", "conv3p_op_backward_f32",
     "conv3p_host_workspace_bytes", "conv3p_host_forward_f32", "conv3p_host_backward_f32",
     "conv3p_status_string", "conv3p_last_cuda_error", "conv3p_abi_version", "conv3p_launch_count",
-    "conv3p_set_engine",
+    "conv3p_set_engine", "conv3p_profile_enable", "conv3p_profile_read",
 ]
 
 
@@ -86,6 +86,10 @@ def _declare(L):
     L.conv3p_launch_count.restype = ll
     L.conv3p_set_engine.argtypes = [i]
     L.conv3p_set_engine.restype = i
+    L.conv3p_profile_enable.argtypes = [i]
+    L.conv3p_profile_enable.restype = i
+    L.conv3p_profile_read.argtypes = [C.c_char_p, sz]
+    L.conv3p_profile_read.restype = ll
 
 
 def lib():

@@ -1,5 +1,9 @@
 // api.cu -- the C ABI of libconv3p_b200.so (declared in include/conv3p_b200.h).
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 #include <cstdio>
 #include <cstring>
 
@@ -19,6 +23,42 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 void count_launch(int n) { g_launches += n; }
 int engine() { return g_engine.load(); }
+
+// ---- optional per-kernel event timing ---------------------------------------------------------------
+struct TimedLaunch {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mutex;
+static std::vector<TimedLaunch> g_prof_records;
+static std::vector<cudaEvent_t> g_prof_pool;
+static std::atomic<int> g_prof_on{0};
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+LaunchTimer::LaunchTimer(const char* name, cudaStream_t s) : slot(-1), stream(s) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  TimedLaunch t{name, prof_event(), prof_event()};
+  cudaEventRecord(t.e0, stream);
+  g_prof_records.push_back(t);
+  slot = (int)g_prof_records.size() - 1;
+}
+
+LaunchTimer::~LaunchTimer() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  if (slot < (int)g_prof_records.size()) cudaEventRecord(g_prof_records[slot].e1, stream);
+}
 
 int check_geom(const conv3p_geom_t* g) {
   if (!g) return CONV3P_ERR_INVALID_ARGUMENT;
@@ -126,6 +166,43 @@ long long conv3p_launch_count(int reset) {
 }
 
 int conv3p_set_engine(int e) { return g_engine.exchange(e); }
+
+int conv3p_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  for (auto& r : g_prof_records) {
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_records.clear();
+  return g_prof_on.exchange(on ? 1 : 0);
+}
+
+long long conv3p_profile_read(char* buf, size_t cap) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  std::map<std::string, std::pair<long long, double> > agg;
+  for (auto& r : g_prof_records) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) {
+      (void)cudaGetLastError();
+      continue;
+    }
+    auto& a = agg[r.name];
+    a.first += 1;
+    a.second += ms;
+  }
+  std::string out;
+  char line[256];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && cap) {
+    size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (long long)g_prof_records.size();
+}
 
 size_t conv3p_plan_bytes(const conv3p_geom_t* geom) {
   conv3p_plan_layout_t L;

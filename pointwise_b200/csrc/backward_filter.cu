@@ -203,13 +203,22 @@ int launch_backward_filter_simt(const conv3p_geom_t* g, const PlanView& v, const
     if (smem > 48 * 1024)
       C3P_CUDA(cudaFuncSetAttribute(k_backward_filter<4, 8>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+    LaunchTimer timer_("k_backward_filter", stream);
     k_backward_filter<4, 8><<<grid, BF_THREADS, smem, stream>>>(a);
+  }
   } else {
+    {
+    LaunchTimer timer_("k_backward_filter", stream);
     k_backward_filter<1, 1><<<grid, BF_THREADS, smem, stream>>>(a);
+  }
   }
   C3P_LAUNCH_CHECK("k_backward_filter");
   const int rt = 256;
-  k_reduce_partials<<<(unsigned)((nW + rt - 1) / rt), rt, 0, stream>>>(a.partial, c.S, nW, grad_filter);
+  {
+    LaunchTimer timer_("k_reduce_partials", stream);
+    k_reduce_partials<<<(unsigned)((nW + rt - 1) / rt), rt, 0, stream>>>(a.partial, c.S, nW, grad_filter);
+  }
   C3P_LAUNCH_CHECK("k_reduce_partials");
   return CONV3P_OK;
 }

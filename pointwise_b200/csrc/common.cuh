@@ -35,6 +35,15 @@ int make_view(const conv3p_geom_t* g, const void* plan, size_t plan_bytes, PlanV
 int check_geom(const conv3p_geom_t* g);
 
 int cuda_fail(cudaError_t e, const char* what);  // records the text, returns CONV3P_ERR_CUDA
+
+// Brackets one kernel launch with CUDA events on its stream while conv3p_profile_enable(1) is in
+// effect (bench.py's live per-kernel timing); a no-op otherwise.
+struct LaunchTimer {
+  LaunchTimer(const char* name, cudaStream_t stream);
+  ~LaunchTimer();
+  int slot;
+  cudaStream_t stream;
+};
 void count_launch(int n = 1);
 int engine();
 

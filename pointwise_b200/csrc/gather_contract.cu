@@ -192,7 +192,10 @@ static int launch_cfg(GCArgs& a, cudaStream_t stream) {
     C3P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (a.total_points + a.P - 1) / a.P;
   dim3 grid((unsigned)tiles, (unsigned)ncol);
-  kern<<<grid, GC_THREADS, smem, stream>>>(a);
+  {
+    LaunchTimer timer_(a.transposed ? "k_gather_contract_bwd_input" : "k_gather_contract_fwd", stream);
+    kern<<<grid, GC_THREADS, smem, stream>>>(a);
+  }
   C3P_LAUNCH_CHECK("k_gather_contract");
   return CONV3P_OK;
 }

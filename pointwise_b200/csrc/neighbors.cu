@@ -327,8 +327,11 @@ int launch_neighbor_search(const conv3p_geom_t* g, const PlanView& v, cudaStream
   C3P_CUDA(cudaMemsetAsync(v.header, 0, sizeof(long long) * H_SLOTS, stream));
   if (pts == 0) return CONV3P_OK;
   const unsigned grid = (unsigned)((pts + NB_WARPS - 1) / NB_WARPS);
-  k_neighbor_search<<<grid, NB_THREADS, 0, stream>>>(g->B, g->N, g->stride[0], g->stride[1],
+  {
+    LaunchTimer timer_("k_neighbor_search", stream);
+    k_neighbor_search<<<grid, NB_THREADS, 0, stream>>>(g->B, g->N, g->stride[0], g->stride[1],
                                                      g->stride[2], g->voxel_size, g->pair_capacity, v);
+  }
   C3P_LAUNCH_CHECK("k_neighbor_search");
   return CONV3P_OK;
 }
@@ -339,9 +342,12 @@ int launch_backward_lists(const conv3p_geom_t* g, const float* points, const Pla
   C3P_CUDA(cudaMemsetAsync(v.header + H_BWD_PAIRS, 0, sizeof(long long), stream));
   if (pts > 0) {
     const unsigned grid = (unsigned)((pts + NB_WARPS - 1) / NB_WARPS);
+    {
+    LaunchTimer timer_("k_backward_lists", stream);
     k_backward_lists<<<grid, NB_THREADS, 0, stream>>>(g->B, g->N, g->stride[0], g->stride[1],
                                                       g->stride[2], g->voxel_size, g->pair_capacity,
                                                       points, v);
+  }
     C3P_LAUNCH_CHECK("k_backward_lists");
   }
   const long long one = 1;

@@ -167,8 +167,11 @@ k_cloud_sort(const float* __restrict__ points, int N, float voxel, float* __rest
 int launch_cloud_sort(const conv3p_geom_t* g, const float* points, const PlanView& v,
                       cudaStream_t stream) {
   if (g->B == 0 || g->N == 0) return CONV3P_OK;
-  k_cloud_sort<<<g->B, SORT_THREADS, 0, stream>>>(points, g->N, g->voxel_size, v.cloud_meta,
+  {
+    LaunchTimer timer_("k_cloud_sort", stream);
+    k_cloud_sort<<<g->B, SORT_THREADS, 0, stream>>>(points, g->N, g->voxel_size, v.cloud_meta,
                                                  v.sorted_key, v.sorted_xyzi, v.sort_tmp);
+  }
   C3P_LAUNCH_CHECK("k_cloud_sort");
   return CONV3P_OK;
 }

@@ -1,0 +1,50 @@
+"""Batch-sharded data parallelism for Conv3p.
+
+Clouds never interact (every loop nest of the reference is inside ``for b``,
+tf_conv3p_atrous.cpp:456, 622), so the batch is split into contiguous shards, one per rank; the
+forward pass and grad_input need no communication, and the weight gradient needs exactly one
+sum-all-reduce -- the multi-GPU analogue of the reference's per-thread grad_filter reduction
+(tf_conv3p_atrous.cpp:709-716).  One process per GPU, ``torch.distributed`` (NCCL on GPUs; gloo in the
+CPU tests of the host logic).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of ``batch`` clouds owned by ``rank``; sizes differ by at most one."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, extra = divmod(batch, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(tensor: torch.Tensor, rank: Optional[int] = None, world: Optional[int] = None) -> torch.Tensor:
+    """This rank's clouds of a [B, ...] tensor (a view)."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    lo, hi = shard_range(tensor.shape[0], rank, world)
+    return tensor[lo:hi]
+
+
+def allreduce_grad_filter(grad_filter: torch.Tensor, group=None, async_op: bool = False):
+    """In-place sum of the weight gradient over all ranks -- the only collective of the path.
+    Messages are small (27*Cin*Cout floats: 8.7 KB at 9->9, 885 KB at 64->128), i.e. latency-bound on
+    NVLink 5 / NVSwitch; it is issued on the compute stream right after the split-K reduction."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(grad_filter, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def conv3p_grad_sharded(grad_from_next, points, input, filter, stride, voxel_size, group=None):
+    """Conv3pGrad on this rank's shard followed by the all-reduce: every rank returns its shard's
+    grad_input and the GLOBAL grad_filter."""
+    from .ops import conv3p_grad
+    gi, gf = conv3p_grad(grad_from_next, points, input, filter, stride, voxel_size)
+    allreduce_grad_filter(gf, group)
+    return gi, gf
