@@ -172,6 +172,16 @@ int conv3p_set_engine(int engine);
 int conv3p_profile_enable(int on);
 long long conv3p_profile_read(char* buf, size_t cap);
 
+/* Self-test of the tensor-core plumbing: D[128,N] = A[128,K] * B[N,K]^T on one CTA with tcgen05
+ * (split != 0: 3xTF32 hi/lo split, fp32-class accuracy; split == 0: plain TF32).  N % 16 == 0,
+ * 16 <= N <= 256, K % 32 == 0.  Device pointers. */
+int conv3p_selftest_tc(const float* A, const float* B, float* D, int N, int K, int split,
+                       conv3p_stream_t stream);
+/* Same with the contraction index outermost in memory (MN-major operands, as in the weight-gradient
+ * kernel): D[128,N] = A^T * B, A[K,128], B[K,N]; N % 32 == 0, K % 8 == 0, K <= 64. */
+int conv3p_selftest_tc_mn(const float* A, const float* B, float* D, int N, int K, int split,
+                          conv3p_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -257,13 +257,13 @@ int conv3p_plan_stats(const conv3p_geom_t* geom, const void* plan, conv3p_plan_s
 
 size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
   if (check_geom(geom) || check_channels(Cin, Cout)) return 0;
-  return backward_filter_scratch_bytes(geom, Cin, Cout) + 256;
+  // [weight panel images | split-K partials of grad_filter]
+  return weight_panel_bytes(Cin, Cout) + backward_filter_scratch_bytes(geom, Cin, Cout) + 256;
 }
 
 int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
                        const float* filter, int Cin, int Cout, float* output, void* scratch,
                        size_t scratch_bytes, conv3p_stream_t stream) {
-  (void)scratch; (void)scratch_bytes;
   int st = check_channels(Cin, Cout);
   if (st) return st;
   PlanView v;
@@ -271,6 +271,10 @@ int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float*
   if (st) return st;
   if ((long long)geom->B * geom->N == 0) return CONV3P_OK;
   if (!input || !filter || !output) return CONV3P_ERR_INVALID_ARGUMENT;
+  if (engine() != 1 && forward_tc_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
+    if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
+    return launch_forward_tc(geom, v, input, filter, Cin, Cout, output, scratch, scratch_bytes, stream);
+  }
   return launch_forward_simt(geom, v, input, filter, Cin, Cout, output, stream);
 }
 
@@ -286,13 +290,21 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
   if (!grad_output && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
   if (grad_input) {
     if (!filter) return CONV3P_ERR_INVALID_ARGUMENT;
-    st = launch_backward_input_simt(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);
+    if (engine() != 1 && backward_input_tc_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
+      if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
+      st = launch_backward_input_tc(geom, v, grad_output, filter, Cin, Cout, grad_input, scratch,
+                                    scratch_bytes, stream);
+    } else {
+      st = launch_backward_input_simt(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);
+    }
     if (st) return st;
   }
   if (grad_filter) {
     if (!input && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
-    st = launch_backward_filter_simt(geom, v, grad_output, input, Cin, Cout, grad_filter, scratch,
-                                     scratch_bytes, stream);
+    const size_t wpb = weight_panel_bytes(Cin, Cout);
+    if (!scratch || scratch_bytes < wpb) return CONV3P_ERR_BUFFER_TOO_SMALL;
+    st = launch_backward_filter_simt(geom, v, grad_output, input, Cin, Cout, grad_filter,
+                                     static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);
     if (st) return st;
   }
   return CONV3P_OK;

@@ -63,6 +63,19 @@ int launch_backward_filter_simt(const conv3p_geom_t* g, const PlanView& v, const
                                 void* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t backward_filter_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout);
 
+// tensor-core (tcgen05, 3xTF32) engine
+bool forward_tc_supported(int N, long long capacity, int Cin, int Cout);
+bool backward_input_tc_supported(int N, long long capacity, int Cin, int Cout);
+int launch_backward_input_tc(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
+                             const float* filter, int Cin, int Cout, float* grad_input, void* scratch,
+                             size_t scratch_bytes, cudaStream_t stream);
+size_t weight_panel_bytes(int Cin, int Cout);
+int launch_prep_weight_panels(const float* filter, void* wp, int Cin, int Cout, int transposed_out,
+                              cudaStream_t stream);
+int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* input, const float* filter,
+                      int Cin, int Cout, float* output, void* scratch, size_t scratch_bytes,
+                      cudaStream_t stream);
+
 }  // namespace c3p
 
 #define C3P_CUDA(expr)                                        \

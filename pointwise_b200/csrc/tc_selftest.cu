@@ -1,0 +1,190 @@
+// tc_selftest.cu -- a one-CTA 3xTF32 GEMM D[128 x N] = A[128 x K] * B[N x K]^T on tcgen05/TMEM.
+// It exercises exactly the plumbing the fused Conv3p tensor-core kernels rely on (operand panels
+// written by ordinary threads in the 128B-swizzled K-major layout, descriptors, kind::tf32 MMA with
+// the hi/lo split, tcgen05.commit -> mbarrier, tcgen05.ld) so that a layout or descriptor mistake is
+// caught by a direct comparison with a float64 product (tests/test_gpu_tc.py).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace c3p {
+
+using namespace tc;
+
+__global__ void __launch_bounds__(128, 1)
+k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K,
+              int split) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = a_hi + 128 * PANEL_ROW_BYTES;
+  unsigned char* b_hi = a_lo + 128 * PANEL_ROW_BYTES;
+  unsigned char* b_lo = b_hi + (size_t)N * PANEL_ROW_BYTES;
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(128, N);
+
+  uint32_t phase = 0;
+  for (int kp = 0; kp < K / PANEL_K; ++kp) {
+    // fill the panels: 16-byte chunks, thread per chunk
+    for (int e = tid; e < 128 * 8; e += 128) {
+      const int r = e >> 3, c = e & 7;
+      const float4 v = *reinterpret_cast<const float4*>(A + (size_t)r * K + kp * PANEL_K + c * 4);
+      float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      if (!split) h = v;
+      *reinterpret_cast<float4*>(a_hi + panel_chunk_offset(r, c)) = h;
+      *reinterpret_cast<float4*>(a_lo + panel_chunk_offset(r, c)) = l;
+    }
+    for (int e = tid; e < N * 8; e += 128) {
+      const int r = e >> 3, c = e & 7;
+      const float4 v = *reinterpret_cast<const float4*>(B + (size_t)r * K + kp * PANEL_K + c * 4);
+      float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      if (!split) h = v;
+      *reinterpret_cast<float4*>(b_hi + panel_chunk_offset(r, c)) = h;
+      *reinterpret_cast<float4*>(b_lo + panel_chunk_offset(r, c)) = l;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+      const uint64_t dah = make_smem_desc(smem_u32(a_hi)), dal = make_smem_desc(smem_u32(a_lo));
+      const uint64_t dbh = make_smem_desc(smem_u32(b_hi)), dbl = make_smem_desc(smem_u32(b_lo));
+#pragma unroll
+      for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
+        const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
+        mma_tf32(tmem, dah + adv, dbh + adv, idesc, (kp | ks) ? 1u : 0u);
+        if (split) {
+          mma_tf32(tmem, dal + adv, dbh + adv, idesc, 1u);
+          mma_tf32(tmem, dah + adv, dbl + adv, idesc, 1u);
+        }
+      }
+      mma_commit(&done_bar);
+    }
+    mbar_wait(&done_bar, phase);
+    phase ^= 1;
+  }
+  tc_fence_after_sync();
+  // epilogue: warp w owns TMEM lanes [32w, 32w+32) == rows
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) D[(size_t)row * N + c0 + j] = v[j];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// MN-major variant: D[128 x N] = A^T * B with A given as [K x 128] and B as [K x N] (contraction index
+// outermost in memory, as the point index is in the weight-gradient kernel).  K <= 64, N % 32 == 0.
+__global__ void __launch_bounds__(128, 1)
+k_tc_selftest_mn(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K,
+                 int split) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t panel = (uint32_t)K * PANEL_ROW_BYTES;   // one panel: K rows x 32 fp32
+  unsigned char* a_hi = smem;                             // 4 panels (M = 128)
+  unsigned char* a_lo = a_hi + 4 * panel;
+  unsigned char* b_hi = a_lo + 4 * panel;                 // N/32 panels
+  unsigned char* b_lo = b_hi + (N / 32) * panel;
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  for (int e = tid; e < K * 32; e += 128) {      // A: K rows x 32 chunks of 16 B
+    const int r = e >> 5, c = e & 31;
+    const float4 v = *reinterpret_cast<const float4*>(A + (size_t)r * 128 + c * 4);
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    if (!split) h = v;
+    const uint32_t o = (uint32_t)(c >> 3) * panel + panel_chunk_offset(r, c & 7);
+    *reinterpret_cast<float4*>(a_hi + o) = h;
+    *reinterpret_cast<float4*>(a_lo + o) = l;
+  }
+  for (int e = tid; e < K * (N / 4); e += 128) {
+    const int r = e / (N / 4), c = e % (N / 4);
+    const float4 v = *reinterpret_cast<const float4*>(B + (size_t)r * N + c * 4);
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    if (!split) h = v;
+    const uint32_t o = (uint32_t)(c >> 3) * panel + panel_chunk_offset(r, c & 7);
+    *reinterpret_cast<float4*>(b_hi + o) = h;
+    *reinterpret_cast<float4*>(b_lo + o) = l;
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after_sync();
+    const uint32_t idesc = make_idesc_tf32_mn(128, N);
+    for (int j = 0; j < K / 8; ++j) {
+      const uint32_t adv = (uint32_t)j * 1024u;
+      const uint64_t dah = make_smem_desc_mn(smem_u32(a_hi) + adv, panel);
+      const uint64_t dal = make_smem_desc_mn(smem_u32(a_lo) + adv, panel);
+      const uint64_t dbh = make_smem_desc_mn(smem_u32(b_hi) + adv, panel);
+      const uint64_t dbl = make_smem_desc_mn(smem_u32(b_lo) + adv, panel);
+      mma_tf32(tmem, dah, dbh, idesc, j ? 1u : 0u);
+      if (split) {
+        mma_tf32(tmem, dal, dbh, idesc, 1u);
+        mma_tf32(tmem, dah, dbl, idesc, 1u);
+      }
+    }
+    mma_commit(&done_bar);
+  }
+  mbar_wait(&done_bar, 0);
+  tc_fence_after_sync();
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(size_t)row * N + c0 + j] = v[j];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace c3p
+
+extern "C" int conv3p_selftest_tc_mn(const float* A, const float* B, float* D, int N, int K, int split,
+                                     conv3p_stream_t stream) {
+  using namespace c3p;
+  if (N < 32 || N > 256 || N % 32 || K < 8 || K > 64 || K % 8) return CONV3P_ERR_INVALID_ARGUMENT;
+  const size_t smem = 2 * (size_t)(4 + N / 32) * K * tc::PANEL_ROW_BYTES;
+  C3P_CUDA(cudaFuncSetAttribute(k_tc_selftest_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tc_selftest_mn<<<1, 128, smem, stream>>>(A, B, D, N, K, split);
+  C3P_LAUNCH_CHECK("k_tc_selftest_mn");
+  return CONV3P_OK;
+}
+
+extern "C" int conv3p_selftest_tc(const float* A, const float* B, float* D, int N, int K, int split,
+                                  conv3p_stream_t stream) {
+  using namespace c3p;
+  if (N < 16 || N > 256 || N % 16 || K < 32 || K % 32) return CONV3P_ERR_INVALID_ARGUMENT;
+  const size_t smem = 2 * 128 * tc::PANEL_ROW_BYTES + 2 * (size_t)N * tc::PANEL_ROW_BYTES + 1024;
+  C3P_CUDA(cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tc_selftest<<<1, 128, smem, stream>>>(A, B, D, N, K, split);
+  C3P_LAUNCH_CHECK("k_tc_selftest");
+  return CONV3P_OK;
+}

@@ -241,10 +241,13 @@ def conv3p_forward(plan: NeighborPlan, input: torch.Tensor, kernel: torch.Tensor
     kernel = _check_cuda_f32(kernel, "kernel")
     Cin, Cout = int(kernel.shape[3]), int(kernel.shape[4])
     out = torch.empty((plan.B, plan.N, Cout), dtype=torch.float32, device=plan.device)
+    L = _lib.lib()
+    nscratch = L.conv3p_scratch_bytes(plan.geom, Cin, Cout)
+    scratch = torch.empty(nscratch, dtype=torch.uint8, device=plan.device)
     with torch.cuda.device(plan.device):
-        _lib.check(_lib.lib().conv3p_forward_f32(plan.geom, _ptr(plan.buffer), _ptr(input), _ptr(kernel),
-                                                 Cin, Cout, _ptr(out), None, 0,
-                                                 _stream_ptr(plan.device)))
+        _lib.check(L.conv3p_forward_f32(plan.geom, _ptr(plan.buffer), _ptr(input), _ptr(kernel),
+                                        Cin, Cout, _ptr(out), _ptr(scratch), nscratch,
+                                        _stream_ptr(plan.device)))
     return out
 
 
@@ -267,11 +270,8 @@ def conv3p_backward(plan: NeighborPlan, grad_output: torch.Tensor, input: torch.
     gi = torch.empty((plan.B, plan.N, Cin), dtype=torch.float32, device=plan.device) \
         if need_input_grad else None
     gf = torch.empty_like(kernel) if need_filter_grad else None
-    scratch = None
-    nscratch = 0
-    if need_filter_grad:
-        nscratch = L.conv3p_scratch_bytes(plan.geom, Cin, Cout)
-        scratch = torch.empty(nscratch, dtype=torch.uint8, device=plan.device)
+    nscratch = L.conv3p_scratch_bytes(plan.geom, Cin, Cout)
+    scratch = torch.empty(nscratch, dtype=torch.uint8, device=plan.device)
     with torch.cuda.device(plan.device):
         _lib.check(L.conv3p_backward_f32(plan.geom, _ptr(plan.buffer), _ptr(grad_output), _ptr(input),
                                          _ptr(kernel), Cin, Cout, _ptr(gi), _ptr(gf), _ptr(scratch),
@@ -329,6 +329,14 @@ def conv3p_grad(grad_from_next, points, input, filter, stride, voxel_size,
     if plan is None:
         plan = NeighborPlan(points, s, v)
     return conv3p_backward(plan, grad_from_next, input, filter)
+
+
+def set_engine(engine: str = "auto") -> str:
+    """Selects the contraction engine: "auto" (tensor cores where the shape allows, else SIMT),
+    "simt" (fp32 CUDA cores only) or "tc".  Returns the previous setting."""
+    names = ["auto", "simt", "tc"]
+    prev = _lib.lib().conv3p_set_engine(names.index(engine))
+    return names[prev]
 
 
 def launch_count(reset: bool = False) -> int:

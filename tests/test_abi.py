@@ -25,7 +25,7 @@ def declared_functions():
 def test_header_symbols_exported(L):
     from pointwise_b200 import _lib
     names = declared_functions()
-    assert len(names) >= 21
+    assert len(names) >= 23
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/conv3p_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == names, "ctypes binding and header disagree"
