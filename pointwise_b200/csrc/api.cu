@@ -258,7 +258,12 @@ int conv3p_plan_stats(const conv3p_geom_t* geom, const void* plan, conv3p_plan_s
 size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
   if (check_geom(geom) || check_channels(Cin, Cout)) return 0;
   // [weight panel images | split-K partials of grad_filter]
-  return weight_panel_bytes(Cin, Cout) + backward_filter_scratch_bytes(geom, Cin, Cout) + 256;
+  size_t filt = backward_filter_scratch_bytes(geom, Cin, Cout);
+  if (backward_filter_tc_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
+    const size_t t = backward_filter_tc_scratch_bytes(geom, Cin, Cout);
+    if (t > filt) filt = t;
+  }
+  return weight_panel_bytes(Cin, Cout) + filt + 256;
 }
 
 int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
@@ -303,8 +308,12 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
     if (!input && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
     const size_t wpb = weight_panel_bytes(Cin, Cout);
     if (!scratch || scratch_bytes < wpb) return CONV3P_ERR_BUFFER_TOO_SMALL;
-    st = launch_backward_filter_simt(geom, v, grad_output, input, Cin, Cout, grad_filter,
+    if (engine() != 1 && backward_filter_tc_supported(geom->N, geom->pair_capacity, Cin, Cout))
+      st = launch_backward_filter_tc(geom, v, grad_output, input, Cin, Cout, grad_filter,
                                      static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);
+    else
+      st = launch_backward_filter_simt(geom, v, grad_output, input, Cin, Cout, grad_filter,
+                                       static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);
     if (st) return st;
   }
   return CONV3P_OK;

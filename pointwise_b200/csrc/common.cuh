@@ -76,6 +76,12 @@ int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* in
                       int Cin, int Cout, float* output, void* scratch, size_t scratch_bytes,
                       cudaStream_t stream);
 
+bool backward_filter_tc_supported(int N, long long capacity, int Cin, int Cout);
+size_t backward_filter_tc_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout);
+int launch_backward_filter_tc(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
+                              const float* input, int Cin, int Cout, float* grad_filter, void* scratch,
+                              size_t scratch_bytes, cudaStream_t stream);
+
 }  // namespace c3p
 
 #define C3P_CUDA(expr)                                        \

@@ -42,17 +42,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-// MN-major view of the same physical panels: a panel [rows x 32 fp32] read as K = rows (8 per MMA, one
-// 1024-byte swizzle atom) and MN = the 32 fp32 of a row; further MN blocks of 32 live in further panels
-// `mn_block_stride` bytes apart (leading byte offset); successive 8-row K groups are 1024 B apart
-// (stride byte offset).  Used by the weight-gradient kernel, whose contraction runs over points.
+// MN-major fp32 operands (contraction index = panel row, as the point index is in the weight-gradient
+// kernel).  For 32-bit MN-major operands the only swizzled layout is "128B swizzle with a 32-byte base"
+// (CUTLASS UMMA::Layout_MN_SW128_32B_Atom): a panel is again [rows x 128 B], row r at r*128, but the
+// swizzle permutes the four 32-byte units of a row, unit u stored at u ^ (r & 3); atoms are 4 rows
+// (512 B).  MN runs along the row (32 fp32 per panel; further MN blocks live in further panels
+// `mn_block_stride` bytes apart = leading byte offset), K runs over rows (stride byte offset 512 B
+// between 4-row atoms; one kind::tf32 MMA consumes 8 rows).
+__host__ __device__ __forceinline__ uint32_t panel_chunk_offset_mn(int row, int chunk) {
+  const uint32_t unit = (((uint32_t)chunk >> 1) ^ ((uint32_t)row & 3u));
+  return (uint32_t)row * PANEL_ROW_BYTES + (((unit << 1) | ((uint32_t)chunk & 1u)) << 4);
+}
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t mn_block_stride) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((mn_block_stride >> 4) & 0x3FFFu) << 16;  // leading byte offset
-  d |= (uint64_t)(1024 >> 4) << 32;                         // stride byte offset
+  d |= (uint64_t)(512 >> 4) << 32;                          // stride byte offset (4-row atoms)
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;                                   // layout type SWIZZLE_128B_BASE32B
   return d;
 }
 __host__ __device__ __forceinline__ uint32_t make_idesc_tf32_mn(int M, int N) {

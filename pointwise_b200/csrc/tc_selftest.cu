@@ -118,7 +118,7 @@ k_tc_selftest_mn(const float* __restrict__ A, const float* __restrict__ B, float
     float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
     if (!split) h = v;
-    const uint32_t o = (uint32_t)(c >> 3) * panel + panel_chunk_offset(r, c & 7);
+    const uint32_t o = (uint32_t)(c >> 3) * panel + panel_chunk_offset_mn(r, c & 7);
     *reinterpret_cast<float4*>(a_hi + o) = h;
     *reinterpret_cast<float4*>(a_lo + o) = l;
   }
@@ -128,7 +128,7 @@ k_tc_selftest_mn(const float* __restrict__ A, const float* __restrict__ B, float
     float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
     if (!split) h = v;
-    const uint32_t o = (uint32_t)(c >> 3) * panel + panel_chunk_offset(r, c & 7);
+    const uint32_t o = (uint32_t)(c >> 3) * panel + panel_chunk_offset_mn(r, c & 7);
     *reinterpret_cast<float4*>(b_hi + o) = h;
     *reinterpret_cast<float4*>(b_lo + o) = l;
   }

@@ -357,17 +357,20 @@ def test_tensor_core_engine_matches_oracle_and_simt(port, Cin, Cout):
     plan = NeighborPlan(dev(pr["points"]), stride, V)
     o32, o64, oabs = port.forward(pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
     r = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
-    outs, gins = {}, {}
+    outs, gins, gfs = {}, {}, {}
     for eng in ("simt", "tc"):
         prev = set_engine(eng)
         try:
             outs[eng] = conv3p_forward(plan, dev(pr["input"]), dev(pr["filter"])).cpu().numpy()
-            gins[eng] = conv3p_backward(plan, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]),
-                                        need_filter_grad=False)[0].cpu().numpy()
+            gi_, gf_ = conv3p_backward(plan, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]))
+            gins[eng], gfs[eng] = gi_.cpu().numpy(), gf_.cpu().numpy()
         finally:
             set_engine(prev)
         assert assert_close_scaled(outs[eng], o64, oabs, RTOL, ATOL, f"forward[{eng}]") < RTOL
         assert assert_close_scaled(gins[eng], r[2], r[3], RTOL, ATOL, f"grad_input[{eng}]") < RTOL
+        assert assert_close_scaled(gfs[eng], r[4], r[5], RTOL, ATOL, f"grad_filter[{eng}]") < RTOL
     assert not np.array_equal(outs["simt"], outs["tc"]), "tensor-core engine was not selected (forward)"
     if Cout % 32 == 0:
         assert not np.array_equal(gins["simt"], gins["tc"]), "tensor-core engine was not selected (grad_input)"
+    if Cout == 128 and Cin <= 64:
+        assert not np.array_equal(gfs["simt"], gfs["tc"]), "tensor-core engine was not selected (grad_filter)"
