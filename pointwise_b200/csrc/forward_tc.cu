@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_gather_mma_tc(const FTArgs a)
         for (int rep = 0; rep < 2; ++rep) {
           const int p = qp + rep * FT_NQ;
           const bool valid = p < 128;
+          if (rep == 1 && !__any_sync(C3P_FULL_MASK, valid)) break;   // warp-uniform
           const int pt = t * 128 + (valid ? p : 0);
           int n = 0, off = 0;
           if (valid) {
@@ -203,12 +204,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_gather_mma_tc(const FTArgs a)
                 }
             }
           }
-          if (!WEIGHTED && n > 0) {
-            const float fn = (float)n;
+          if (!WEIGHTED && n > 1) {
+            const float inv = __fdiv_rn(1.f, (float)n);   // one divide per cell, not one per channel
 #pragma unroll
             for (int kc = 0; kc < NKC; ++kc) {
-              acc[kc].x = __fdiv_rn(acc[kc].x, fn); acc[kc].y = __fdiv_rn(acc[kc].y, fn);
-              acc[kc].z = __fdiv_rn(acc[kc].z, fn); acc[kc].w = __fdiv_rn(acc[kc].w, fn);
+              acc[kc].x *= inv; acc[kc].y *= inv; acc[kc].z *= inv; acc[kc].w *= inv;
             }
           }
           if (rep == 0) {  // ring slots of this (f,t) group must be drained by the tensor core first
@@ -277,41 +277,51 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_gather_mma_tc(const FTArgs a)
     }
   } else if (warp == FT_NPW) {
     // =========================== MMA issuer (one thread) ============================================
+    // No divisions in this loop: ring positions are tracked incrementally and descriptors are derived
+    // from per-ring bases with one add.
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, Cout);
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(a_base)), w_desc0 = make_smem_desc(smem_u32(w_base));
+      const uint64_t a_lo_off = (uint64_t)((128 * PANEL_ROW_BYTES) >> 4);
+      const uint64_t w_lo_off = (uint64_t)(((uint32_t)Cout * PANEL_ROW_BYTES) >> 4);
+      const uint64_t a_step = (uint64_t)(FT_A_STAGE >> 4), w_step = (uint64_t)(w_slot_bytes >> 4);
       unsigned started = 0;
-      int s = 0, u = 0;
+      int aslot = 0, wslot0 = -NKC;
+      uint32_t aphase = 0, wphase0 = 0;
       for (int f = 0; f < C3P_NCELL; ++f) {
         const unsigned act = active[f];
         if (!act) continue;
         const int t_first = __ffs(act) - 1, t_last = 31 - __clz(act);
-        for (int kb = 0; kb < a.nkb; ++kb, u += NKC)
-        for (int t = 0; t < T; ++t) {
-          if (!((act >> t) & 1u)) continue;
-          for (int kc = 0; kc < NKC; ++kc) {
-            const int wu = u + kc, wslot = wu % NWS;
-            if (t == t_first) mbar_wait(&w_full[wslot], (uint32_t)((wu / NWS) & 1));
-            const int slot = s % FT_NAS;
-            mbar_wait(&a_full[slot], (uint32_t)((s / FT_NAS) & 1));
-            tc_fence_after_sync();
-            const uint32_t a_hi = smem_u32(a_base + (size_t)slot * FT_A_STAGE);
-            const uint32_t a_lo = a_hi + 128 * PANEL_ROW_BYTES;
-            const uint32_t w_hi = smem_u32(w_base + (size_t)wslot * w_slot_bytes);
-            const uint32_t w_lo = w_hi + (uint32_t)Cout * PANEL_ROW_BYTES;
-            const uint64_t dah = make_smem_desc(a_hi), dal = make_smem_desc(a_lo);
-            const uint64_t dwh = make_smem_desc(w_hi), dwl = make_smem_desc(w_lo);
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          wslot0 += NKC;
+          if (wslot0 >= NWS) { wslot0 -= NWS; wphase0 ^= 1u; }
+          for (int t = 0; t < T; ++t) {
+            if (!((act >> t) & 1u)) continue;
             const uint32_t d = tmem + (uint32_t)(t * Cout);
-#pragma unroll
-            for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
-              const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
-              mma_tf32(d, dah + adv, dwh + adv, idesc, (((started >> t) & 1u) | (unsigned)ks) ? 1u : 0u);
-              mma_tf32(d, dal + adv, dwh + adv, idesc, 1u);
-              mma_tf32(d, dah + adv, dwl + adv, idesc, 1u);
-            }
+            uint32_t acc_flag = (started >> t) & 1u;
             started |= 1u << t;
-            mma_commit(&a_empty[slot]);
-            if (t == t_last) mma_commit(&w_empty[wslot]);
-            ++s;
+#pragma unroll
+            for (int kc = 0; kc < NKC; ++kc) {
+              int wslot = wslot0 + kc;
+              uint32_t wphase = wphase0;
+              if (wslot >= NWS) { wslot -= NWS; wphase ^= 1u; }
+              if (t == t_first) mbar_wait(&w_full[wslot], wphase);
+              mbar_wait(&a_full[aslot], aphase);
+              tc_fence_after_sync();
+              const uint64_t dah = a_desc0 + (uint64_t)aslot * a_step, dal = dah + a_lo_off;
+              const uint64_t dwh = w_desc0 + (uint64_t)wslot * w_step, dwl = dwh + w_lo_off;
+#pragma unroll
+              for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                mma_tf32(d, dah + adv, dwh + adv, idesc, acc_flag);
+                mma_tf32(d, dal + adv, dwh + adv, idesc, 1u);
+                mma_tf32(d, dah + adv, dwl + adv, idesc, 1u);
+                acc_flag = 1u;
+              }
+              mma_commit(&a_empty[aslot]);
+              if (t == t_last) mma_commit(&w_empty[wslot]);
+              if (++aslot == FT_NAS) { aslot = 0; aphase ^= 1u; }
+            }
           }
         }
       }

@@ -1,0 +1,23 @@
+"""Ablation timing of the tensor-core forward kernel: engine 8|1 skips gathers, 8|2 skips MMAs."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from bench import VOXEL, WORKLOADS
+from pointwise_b200 import NeighborPlan, _lib, conv3p_forward, conv3p_backward
+from pointwise_b200.synth import make_problem
+B, N, Cin, Cout, stride, dist = WORKLOADS["headline"]
+pr = {k: torch.from_numpy(v).cuda() for k, v in make_problem(B, N, Cin, Cout, dist, seed=0).items()}
+plan = NeighborPlan(pr["points"], stride, VOXEL).ensure_backward()
+L = _lib.lib()
+for eng, name in [(0, "auto"), (1, "simt")]:
+    L.conv3p_set_engine(eng)
+    for fn, label in [(lambda: conv3p_forward(plan, pr["input"], pr["filter"]), "fwd"),
+                      (lambda: conv3p_backward(plan, pr["grad_out"], pr["input"], pr["filter"]), "bwd")]:
+        for _ in range(2): fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5): fn()
+        e1.record(); torch.cuda.synchronize()
+        print(f"{name:10s} {label:7s} {e0.elapsed_time(e1)/5:.3f} ms")
+L.conv3p_set_engine(0)
