@@ -129,29 +129,20 @@ def cpu_step(chk, pr, stride):
     chk.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, VOXEL)
 
 
-def run_cpu_baseline(workload: str, budget_s: float = 12.0):
-    """One bounded sample (about `budget_s` of CPU work) -> cpu_baseline dict."""
-    chk = cpu_checker()
-    cores = os.cpu_count() or 1
-    _, N, Cin, Cout, _, _ = WORKLOADS[workload]
-    pr1, stride = cpu_sample(workload, 1)
-    t0 = time.perf_counter()
-    cpu_step(chk, pr1, stride)                      # also warms the OpenMP team
-    t1 = time.perf_counter() - t0                   # one cloud on one thread
-    threads = min(cores, chk.threads)
-    waves = max(1, int(budget_s / max(t1, 1e-3)))
-    clouds = int(min(threads * waves, 8 * threads, 256))
-    clouds = max(clouds, threads)
-    pr, stride = cpu_sample(workload, clouds)
-    best = None
-    for _ in range(2 if t1 * clouds / threads < budget_s / 2 else 1):
-        t0 = time.perf_counter()
-        cpu_step(chk, pr, stride)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return {"value": clouds * N / best, "unit": UNIT, "cores": threads, "kind": chk.kind,
-            "sample": f"{clouds} clouds x {N} points, {Cin}->{Cout}, fwd+bwd, best of runs, {best:.2f} s",
-            "host_cpus": cores}
+def run_cpu_baseline(workload: str):
+    """The reference CPU op timed on a bounded sample of the workload, in a clean subprocess (no CUDA
+    context, no torch threads): exactly `bench.py --impl reference --steps 2 --warmup 1`."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--workload", workload]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable",
+            "sample": (out.stderr or "no output")[-200:]}
 
 
 def reference_arm(args):
@@ -328,6 +319,10 @@ def gpu_arm(args):
             dist.destroy_process_group()
         return
     pk = peaks()
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {})
     top = max(kern, key=lambda k: kern[k][1]) if kern else None
     roof = None
     kernels = {}
@@ -343,7 +338,9 @@ def gpu_arm(args):
         ab = algorithmic_bytes(top, pts, Cin, Cout, kbar, kbar_b)
         flops = 2.0 * 27 * Cin * Cout * pts
         roof = {"kernel": top, "bound": "hbm", "achieved": ab / avg_s / 1e9, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "frac": ab / avg_s / 1e9 / pk["hbm_gbs"], "traffic": None,
+                "unit": "GB/s", "frac": ab / avg_s / 1e9 / pk["hbm_gbs"],
+                "traffic": traffic.get(top, {}).get("dram_bytes_per_launch"),
+                "algorithmic_bytes_per_launch": ab,
                 "peak_source": pk["source"] + " (MEASURED_PEAKS.json hbm_gbs)",
                 "model": "gather model G (SURVEY 8d): list entries x (index + row bytes) + per-point I/O",
                 "dense_tflops": flops / avg_s / 1e12,
