@@ -71,7 +71,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -135,7 +135,7 @@ def run_cpu_baseline(workload: str):
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
            "--workload", workload]
     env = dict(os.environ)
-    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS"):
         env.pop(k, None)
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
     for ln in reversed(out.stdout.strip().splitlines()):
@@ -242,21 +242,6 @@ def gpu_arm(args):
             allreduce_grad_filter(gf)
         return plan, y, gi, gf
 
-    out_host = {"y": torch.empty((hi - lo, N, Cout), dtype=torch.float32).pin_memory(),
-                "gi": torch.empty((hi - lo, N, Cin), dtype=torch.float32).pin_memory(),
-                "gf": torch.empty((3, 3, 3, Cin, Cout), dtype=torch.float32).pin_memory()}
-
-    def step_e2e():
-        d = {k: v.to(device, non_blocking=True) for k, v in host.items()}
-        plan = NeighborPlan(d["points"], stride, VOXEL, check=False, capacity=capacity)
-        y = conv3p_forward(plan, d["input"], d["filter"])
-        gi, gf = conv3p_backward(plan, d["grad_out"], d["input"], d["filter"])
-        if world > 1:
-            allreduce_grad_filter(gf)
-        out_host["y"].copy_(y, non_blocking=True)
-        out_host["gi"].copy_(gi, non_blocking=True)
-        out_host["gf"].copy_(gf, non_blocking=True)
-
     # capacity: learned once (checked build), then every step runs without a host read-back
     probe = NeighborPlan(devt["points"], stride, VOXEL).ensure_backward()
     st = probe.read_stats()
@@ -286,11 +271,11 @@ def gpu_arm(args):
             ms = float(t.item())
         return ms / steps
 
-    for _ in range(max(3, args.warmup)):
-        step_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # nvidia-smi needs ~0.1 s to start: begin before the warm-up steps
+    for _ in range(max(3, args.warmup)):
+        step_device()
     launch_count(reset=True)
     L.conv3p_profile_enable(1)
     ms_step = timed(step_device, args.steps)
@@ -307,12 +292,39 @@ def gpu_arm(args):
         kern[name] = (int(n), float(total))
     value = B_global * N / (ms_step * 1e-3)
 
-    # e2e (host buffers)
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, max(3, args.steps // 2))
-    h2d = sum(v.numel() * 4 for v in host.values())
-    d2h = sum(v.numel() * 4 for v in out_host.values())
+    # e2e (host buffers): every step copies its pinned-host inputs to the device, rebuilds the plan, runs
+    # forward + backward (+ the all-reduce) and copies output / grad_input / grad_filter back to pinned host
+    # memory; copies of neighbouring steps overlap the kernels (three streams, double-buffered staging).
+    from pointwise_b200.host_api import HostConv3p
+    pipe = HostConv3p(hi - lo, N, Cin, Cout, stride, VOXEL, device=device, capacity=capacity)
+    ar = allreduce_grad_filter if world > 1 else None
+
+    def run_e2e(steps):
+        tickets = []
+        for _ in range(steps):
+            tickets.append(pipe.submit(host["points"], host["input"], host["filter"], host["grad_out"], ar))
+            if len(tickets) >= 2:
+                pipe.fetch(tickets[-2])
+        pipe.fetch(tickets[-1])
+
+    run_e2e(3)
+    e2e_steps = max(4, args.steps)
+    barrier()
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_e2e(e2e_steps)
+    torch.cuda.synchronize()
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / e2e_steps
+    wall_e2e = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
 
     if rank != 0:
         if world > 1:
@@ -353,7 +365,8 @@ def gpu_arm(args):
                               mean_backward_pairs=round(kbar_b, 2), mean_nonempty_cells=round(nbins, 2)),
         "clocks": clocks,
         "e2e": {"value": B_global * N / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "wall_ms_per_step": wall_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "pointwise_b200.host_api.HostConv3p (pinned host in/out, copies overlapped with compute)"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "kernels": kernels,
@@ -375,6 +388,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread it can
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         reference_arm(args)
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))

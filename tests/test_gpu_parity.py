@@ -374,3 +374,24 @@ def test_tensor_core_engine_matches_oracle_and_simt(port, Cin, Cout):
         assert not np.array_equal(gins["simt"], gins["tc"]), "tensor-core engine was not selected (grad_input)"
     if Cout == 128 and Cin <= 64:
         assert not np.array_equal(gfs["simt"], gfs["tc"]), "tensor-core engine was not selected (grad_filter)"
+
+
+def test_host_pipeline_matches_direct_calls():
+    """HostConv3p (pinned host in/out, overlapped copies) returns exactly what the direct calls return."""
+    from pointwise_b200 import NeighborPlan, conv3p_backward, conv3p_forward
+    from pointwise_b200.host_api import HostConv3p
+    B, N, Cin, Cout, stride = 3, 900, 9, 13, (2, 2, 2)
+    pipe = HostConv3p(B, N, Cin, Cout, stride, V)
+    probs = [make_problem(B, N, Cin, Cout, "room", seed=30 + i) for i in range(4)]
+    host = [{k: torch.from_numpy(v).pin_memory() for k, v in pr.items()} for pr in probs]
+    tickets, results = [], []
+    for h in host:
+        tickets.append(pipe.submit(h["points"], h["input"], h["filter"], h["grad_out"]))
+        if len(tickets) >= 2:
+            results.append([t.clone() for t in pipe.fetch(tickets[-2])])
+    results.append([t.clone() for t in pipe.fetch(tickets[-1])])
+    for pr, (y, gi, gf) in zip(probs, results):
+        plan = NeighborPlan(dev(pr["points"]), stride, V)
+        y0 = conv3p_forward(plan, dev(pr["input"]), dev(pr["filter"]))
+        gi0, gf0 = conv3p_backward(plan, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]))
+        assert torch.equal(y, y0.cpu()) and torch.equal(gi, gi0.cpu()) and torch.equal(gf, gf0.cpu())
