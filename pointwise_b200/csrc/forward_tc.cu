@@ -359,13 +359,26 @@ struct FTConfig {
 };
 
 // Csrc = contraction width per cell (Cin forward, Cout backward), Nout = output width.
-static bool ft_config(int N, long long capacity, int Csrc, int Nout, FTConfig* c) {
+static bool ft_config(int N, long long capacity, int Csrc, int Nout, FTConfig* c, long long points = 0) {
   if (N > 65535) return false;                // per-point list offsets are kept as 16-bit prefixes
   if (capacity >= (1LL << 32)) return false;  // list starts are kept as 32-bit offsets
   if (Csrc % 32 || Nout % 16 || Csrc < 32 || Nout < 16 || Nout > 256) return false;
   c->NKC = (Csrc % 64 == 0) ? 2 : 1;
   c->nkb = Csrc / (32 * c->NKC);
   c->T = 512 / Nout >= 4 ? 4 : (512 / Nout);
+  // Wave quantisation: with one CTA per SM the launch takes ceil(tiles/SMs) rounds of T sub-tiles each;
+  // a smaller T can need fewer sub-tile rounds in total (e.g. 262,144 points on 148 SMs: T=4 -> 4x4 = 16,
+  // T=3 -> 5x3 = 15).  Weight panels are re-streamed per tile, so only T >= 3 is considered.
+  if (points > 0 && c->T == 4) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    (void)cudaGetLastError();
+    auto rounds = [&](int T) {
+      const long long tiles = (points + (long long)T * 128 - 1) / ((long long)T * 128);
+      return ((tiles + sms - 1) / sms) * T;
+    };
+    if (rounds(3) < rounds(4)) c->T = 3;
+  }
   c->NWS = c->NKC + 1;
   c->smem = ft_smem_bytes(Nout, c->T, c->NWS);
   return c->smem <= 227 * 1024 - 1024;
@@ -419,7 +432,7 @@ int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* in
                       int Cin, int Cout, float* output, void* scratch, size_t scratch_bytes,
                       cudaStream_t stream) {
   FTConfig c;
-  if (!ft_config(g->N, g->pair_capacity, Cin, Cout, &c)) return CONV3P_ERR_UNSUPPORTED;
+  if (!ft_config(g->N, g->pair_capacity, Cin, Cout, &c, (long long)g->B * g->N)) return CONV3P_ERR_UNSUPPORTED;
   if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
   int st = launch_prep_weight_panels(filter, scratch, Cin, Cout, 0, stream);
   if (st) return st;
@@ -436,7 +449,7 @@ int launch_backward_input_tc(const conv3p_geom_t* g, const PlanView& v, const fl
                              const float* filter, int Cin, int Cout, float* grad_input, void* scratch,
                              size_t scratch_bytes, cudaStream_t stream) {
   FTConfig c;
-  if (!ft_config(g->N, g->pair_capacity, Cout, Cin, &c)) return CONV3P_ERR_UNSUPPORTED;
+  if (!ft_config(g->N, g->pair_capacity, Cout, Cin, &c, (long long)g->B * g->N)) return CONV3P_ERR_UNSUPPORTED;
   if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
   int st = launch_prep_weight_panels(filter, scratch, Cin, Cout, 1, stream);
   if (st) return st;

@@ -395,3 +395,29 @@ def test_host_pipeline_matches_direct_calls():
         y0 = conv3p_forward(plan, dev(pr["input"]), dev(pr["filter"]))
         gi0, gf0 = conv3p_backward(plan, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]))
         assert torch.equal(y, y0.cpu()) and torch.equal(gi, gi0.cpu()) and torch.equal(gf, gf0.cpu())
+
+
+@pytest.mark.parametrize("B,N", [(0, 16), (3, 0), (0, 0)])
+def test_empty_inputs(B, N):
+    """Empty batches / empty clouds: empty outputs, zero weight gradient, no crash."""
+    from pointwise_b200 import conv3p
+    P = torch.zeros(B, N, 3, device="cuda")
+    X = torch.zeros(B, N, 5, device="cuda", requires_grad=True)
+    W = torch.randn(3, 3, 3, 5, 7, device="cuda", requires_grad=True)
+    y = conv3p(P, X, W, [1, 1, 1], [0.1])
+    assert y.shape == (B, N, 7)
+    y.sum().backward()
+    assert X.grad.shape == (B, N, 5)
+    assert W.grad.shape == W.shape and float(W.grad.abs().max()) == 0.0
+
+
+def test_ragged_cloud_sizes_through_tiles(port):
+    """Cloud sizes that straddle tile boundaries of both engines (N = 1, 127, 129, 513 in one sweep)."""
+    from pointwise_b200 import NeighborPlan, conv3p_forward
+    for N in (1, 127, 129, 513):
+        pr = make_problem(3, N, 32, 32, "cube", seed=N)
+        pr["points"] *= 0.3                       # dense enough to have neighbours
+        plan = NeighborPlan(dev(pr["points"]), 1, V)
+        out = conv3p_forward(plan, dev(pr["input"]), dev(pr["filter"])).cpu().numpy()
+        o32, o64, oabs = port.forward(pr["points"], pr["input"], pr["filter"], 1, V, with64=True)
+        assert_close_scaled(out, o64, oabs, RTOL, ATOL, f"forward N={N}")
