@@ -1,0 +1,103 @@
+"""Drop-in consumers of the operator: PyTorch restatements of the reference's two PointConvNets
+(SURVEY section 8f, rows N1/N2).  They exist to prove the drop-in claim at the reference's own call sites and to
+exercise plan sharing; they are not part of the hot path.
+
+* ``PointConvNetCls``  -- pointcnn2_acsd.py:33-90: four Conv3p layers (Cin->9, 9->9 x3, strides 1..4), SELU, concat
+  of the 36 channels, flatten [B, N*36] -> FC 512 (SELU) -> alpha-dropout -> FC num_class (SELU);
+  sparse softmax cross-entropy.
+* ``PointConvNetSeg``  -- scene_seg/pointcnn_scene_seg_acsd.py:32-71: four 9-channel layers (strides 1..4), concat,
+  one 36->num_class layer at stride 1, every layer followed by SELU; softmax cross-entropy per point.
+
+A ``PlanCache`` builds one neighbour plan per (points, stride) and hands it to every layer that needs it and to
+the backward pass; the reference rebuilds its grid twice per layer per step (tf_conv3p_atrous.cpp:463, 629).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .ops import NeighborPlan, conv3p, parse_stride, parse_voxel
+
+
+class PlanCache:
+    """Neighbour plans of ONE batch of points, keyed by stride (voxel size fixed)."""
+
+    def __init__(self, points: torch.Tensor, voxel_size=0.1):
+        self.points = points
+        self.voxel = parse_voxel(voxel_size)
+        self.plans = {}
+
+    def get(self, stride) -> NeighborPlan:
+        s = parse_stride(stride)
+        if s not in self.plans:
+            self.plans[s] = NeighborPlan(self.points, s, self.voxel)
+        return self.plans[s]
+
+
+def _filter(cin: int, cout: int) -> nn.Parameter:
+    # tf.get_variable default: glorot-uniform over the [3,3,3,cin,cout] tensor (fan = 27*cin, 27*cout)
+    w = torch.empty(3, 3, 3, cin, cout)
+    bound = math.sqrt(6.0 / (27 * cin + 27 * cout))
+    return nn.Parameter(w.uniform_(-bound, bound))
+
+
+class PointConvNetCls(nn.Module):
+    """pointcnn2_acsd.py:33-77."""
+
+    def __init__(self, num_class: int, num_points: int, in_channels: int, voxel_size: float = 0.1):
+        super().__init__()
+        self.voxel = voxel_size
+        self.filters = nn.ParameterList([_filter(in_channels, 9), _filter(9, 9), _filter(9, 9), _filter(9, 9)])
+        self.fc1 = nn.Linear(num_points * 36, 512)
+        self.fc2 = nn.Linear(512, num_class)
+
+    def model(self, points_tensor: torch.Tensor, input_tensor: torch.Tensor, is_training: bool = True):
+        plans = PlanCache(points_tensor, self.voxel)
+        x, feats = input_tensor, []
+        for i, w in enumerate(self.filters):                      # strides 1,2,3,4 -- :48-67
+            stride = [i + 1] * 3
+            x = F.selu(conv3p(points_tensor, x, w, stride, [self.voxel], plan=plans.get(stride)))
+            feats.append(x)
+        feat = torch.cat(feats, dim=2)                            # :69
+        view = feat.reshape(feat.shape[0], -1)                    # :70
+        fc1 = F.selu(self.fc1(view))                              # :71
+        drop = F.alpha_dropout(fc1, p=0.5, training=is_training)  # selu.dropout_selu, :73
+        return F.selu(self.fc2(drop))                             # :75
+
+    forward = model
+
+    @staticmethod
+    def loss(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        return F.cross_entropy(logits, labels)                    # sparse softmax CE, mean -- :88-89
+
+
+class PointConvNetSeg(nn.Module):
+    """scene_seg/pointcnn_scene_seg_acsd.py:39-58."""
+
+    def __init__(self, num_class: int, in_channels: int, voxel_size: float = 0.1):
+        super().__init__()
+        self.voxel = voxel_size
+        self.filters = nn.ParameterList([_filter(in_channels, 9), _filter(9, 9), _filter(9, 9), _filter(9, 9),
+                                         _filter(36, num_class)])
+
+    def model(self, points_tensor: torch.Tensor, input_tensor: torch.Tensor, is_training: bool = True):
+        plans = PlanCache(points_tensor, self.voxel)
+        x, feats = input_tensor, []
+        for i in range(4):                                         # :51-54
+            stride = [i + 1] * 3
+            x = F.selu(conv3p(points_tensor, x, self.filters[i], stride, [self.voxel], plan=plans.get(stride)))
+            feats.append(x)
+        concat = torch.cat(feats, dim=2)                           # :56
+        # layer 5 reuses the stride-1 plan of layer 1
+        return F.selu(conv3p(points_tensor, concat, self.filters[4], [1, 1, 1], [self.voxel],
+                             plan=plans.get([1, 1, 1])))           # :57
+
+    forward = model
+
+    @staticmethod
+    def loss(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        # tf.losses.softmax_cross_entropy(one_hot, logits): mean over all points -- :66-67
+        return F.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1))

@@ -150,6 +150,9 @@ FEATURE_CASES = [
     (1, 1500, 64, 128, (1, 1, 1), "room", 0.05),    # asymmetric pairs, N not a tile multiple
     (2, 512, 5, 7, (1, 2, 3), "cube", 0.05),
     (1, 300, 40, 300, (1, 1, 1), "room", None),     # Cout beyond one column block
+    (1, 16384, 9, 9, (1, 1, 1), "room", None),      # BASELINE sweep: N=16k (K ~ 190 per point)
+    (1, 4096, 64, 64, (2, 2, 2), "room", None),     # BASELINE sweep: C=64, dilated
+    (1, 1024, 256, 256, (1, 1, 1), "room", None),   # BASELINE sweep: C=256
     (1, 1, 4, 4, (1, 1, 1), "cube", None),
 ]
 
