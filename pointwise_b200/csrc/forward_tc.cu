@@ -18,12 +18,13 @@
 // weight loader + TMEM allocator.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_gather.cuh"
 
 namespace c3p {
 
 using namespace tc;
 
-constexpr int FT_NPW = 20;                 // producer warps
+constexpr int FT_NPW = 16;                 // producer warps
 constexpr int FT_NQ = FT_NPW * 4;          // quarter-warps: one point-row segment each
 constexpr int FT_THREADS = (FT_NPW + 2) * 32;
 constexpr int FT_NAS = 3;                  // A ring stages
@@ -33,6 +34,9 @@ constexpr int FT_MAX_NKC = 4;
 // One kernel serves the forward pass (src = input, lists = forward lists, per-cell mean) and the input
 // gradient (src = grad_out, lists = backward lists with per-entry weights 1/count(ii,f'), panels = W
 // itself): out[p, n] = sum_f sum_k A_f[p, k] * Wpanel_f[n, k].
+// phase timers of the producer loop (cycles, warp 0 of every CTA); filled only when engine debug bit 32 is set
+__device__ unsigned long long g_phase_cycles[8];
+
 struct FTArgs {
   const float* src;         // gathered rows [B*N, Csrc]
   const unsigned char* wp;  // weight panel images [27][Csrc/32][hi,lo][Nout][128 B]
@@ -45,6 +49,7 @@ struct FTArgs {
   const float4* sorted_xyzi;
   long long total_points, capacity;
   int N, Csrc, Nout, nkb, T, NWS;  // nkb = K batches of NKC 32-channel panels
+  int debug;
 };
 
 // weights [27][Cin][Cout] -> panel images: for (f, kc, hl) a [Cout rows x 32 k] K-major swizzled panel
@@ -72,7 +77,6 @@ __global__ void k_prep_weight_panels(const float* __restrict__ filter, unsigned 
   }
 }
 
-__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 template <int NKC, bool WEIGHTED>
 __global__ void __launch_bounds__(FT_THREADS, 1) k_gather_mma_tc(const FTArgs a) {
@@ -142,106 +146,170 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_gather_mma_tc(const FTArgs a)
 
   if (warp < FT_NPW) {
     // =========================== producers: gather -> mean -> hi/lo -> operand panels ===============
-    const int q = warp * 4 + (lane >> 3);  // quarter-warp id
-    const int l8 = lane & 7;               // 16-byte chunk of the 128-byte row segment
-    int s = 0, g = 0;
-    for (int f = 0; f < C3P_NCELL; ++f) {
-      const unsigned act = active[f];
-      if (!act) continue;
-      for (int kb = 0; kb < a.nkb; ++kb)
-      for (int t = 0; t < T; ++t) {
-        if (!((act >> t) & 1u)) continue;
-        const int qp = (q + g * 32) % FT_NQ;
-        // Every lane runs both repetitions and all member rounds (trip counts are made warp-uniform)
-        // because the row-id broadcast below is a warp-wide shuffle.
-#pragma unroll 1
-        for (int rep = 0; rep < 2; ++rep) {
-          const int p = qp + rep * FT_NQ;
-          const bool valid = p < 128;
-          if (rep == 1 && !__any_sync(C3P_FULL_MASK, valid)) break;   // warp-uniform
-          const int pt = t * 128 + (valid ? p : 0);
-          int n = 0, off = 0;
-          if (valid) {
-            off = pre16[pt * 28 + f];
-            n = (int)pre16[pt * 28 + f + 1] - off;
-          }
-          int nmax = max(n, __shfl_xor_sync(C3P_FULL_MASK, n, 8));
-          nmax = max(nmax, __shfl_xor_sync(C3P_FULL_MASK, nmax, 16));
-          float4 acc[NKC];
-#pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) acc[kc] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const size_t lbase = valid ? (size_t)beg[pt] + off : 0;
-          const int* list = a.rows + lbase;
-          for (int m0 = 0; m0 < nmax; m0 += 8) {
-            const int nr = max(0, min(8, n - m0));
-            const int nrmax = min(8, nmax - m0);
-            const int my_id = l8 < nr ? __ldg(list + m0 + l8) : 0;
-            float my_w = 1.f;
-            if (WEIGHTED) my_w = l8 < nr ? __ldg(a.weights + lbase + m0 + l8) : 0.f;
-            for (int mb = 0; mb < nrmax; mb += 4) {
-              float4 v[4][NKC];
-              float wv[4];
-#pragma unroll
-              for (int m = 0; m < 4; ++m) {
-                const int id = __shfl_sync(C3P_FULL_MASK, my_id, mb + m, 8);
-                wv[m] = WEIGHTED ? __shfl_sync(C3P_FULL_MASK, my_w, mb + m, 8) : 1.f;
-                const float* src = a.src + (size_t)id * a.Csrc + (kb * NKC) * PANEL_K + l8 * 4;
-#pragma unroll
-                for (int kc = 0; kc < NKC; ++kc)
-                  v[m][kc] = (mb + m < nr) ? ldg_f4(src + kc * PANEL_K) : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-#pragma unroll
-              for (int m = 0; m < 4; ++m)
-#pragma unroll
-                for (int kc = 0; kc < NKC; ++kc) {
-                  if (WEIGHTED) {
-                    acc[kc].x = fmaf(wv[m], v[m][kc].x, acc[kc].x); acc[kc].y = fmaf(wv[m], v[m][kc].y, acc[kc].y);
-                    acc[kc].z = fmaf(wv[m], v[m][kc].z, acc[kc].z); acc[kc].w = fmaf(wv[m], v[m][kc].w, acc[kc].w);
-                  } else {
-                    acc[kc].x += v[m][kc].x; acc[kc].y += v[m][kc].y;
-                    acc[kc].z += v[m][kc].z; acc[kc].w += v[m][kc].w;
-                  }
-                }
-            }
-          }
-          if (!WEIGHTED && n > 1) {
-            const float inv = __fdiv_rn(1.f, (float)n);   // one divide per cell, not one per channel
-#pragma unroll
-            for (int kc = 0; kc < NKC; ++kc) {
-              acc[kc].x *= inv; acc[kc].y *= inv; acc[kc].z *= inv; acc[kc].w *= inv;
-            }
-          }
-          if (rep == 0) {  // ring slots of this (f,t) group must be drained by the tensor core first
-#pragma unroll
-            for (int kc = 0; kc < NKC; ++kc) {
-              const int st = s + kc, use = st / FT_NAS;
-              if (use >= 1) mbar_wait(&a_empty[st % FT_NAS], (uint32_t)((use - 1) & 1));
-            }
-          }
-          if (valid) {
-#pragma unroll
-            for (int kc = 0; kc < NKC; ++kc) {
-              unsigned char* stage = a_base + (size_t)((s + kc) % FT_NAS) * FT_A_STAGE;
-              const float4 h = make_float4(tf32_hi(acc[kc].x), tf32_hi(acc[kc].y), tf32_hi(acc[kc].z),
-                                           tf32_hi(acc[kc].w));
-              const float4 lo = make_float4(acc[kc].x - h.x, acc[kc].y - h.y, acc[kc].z - h.z,
-                                            acc[kc].w - h.w);
-              const uint32_t o = panel_chunk_offset(p, l8);
-              *reinterpret_cast<float4*>(stage + o) = h;
-              *reinterpret_cast<float4*>(stage + 128 * PANEL_ROW_BYTES + o) = lo;
-            }
+    // Quarter-warp q serves rows (q + 32*g) mod NQ (+ NQ) of group g; lane l8 owns one 16-byte chunk of the
+    // row segment.  The loop is software-pipelined over (group, repetition) slots: the list ids of the next
+    // slot are loaded while the rows of the current slot are in flight (select on the ADDRESS, so nothing
+    // waits on the prefetch), and up to eight members x NKC panels of a row are in flight at once.
+    const int q = warp * 4 + (lane >> 3);
+    const int l8 = lane & 7;
+    struct Slot {
+      int p, n;          // row in the sub-tile (or -1), members of its cell
+      uint32_t lb;       // list position
+      int ids;           // lane l8: row id of member l8 (padding lanes: member 0)
+      float w;           // lane l8: weight of member l8
+    };
+    int gf = -1, gkb = a.nkb - 1, gt = T - 1;   // group iterator (cell, K batch, sub-tile)
+    unsigned gact = 0;
+    auto advance = [&](int& f_, int& kb_, int& t_, unsigned& act_) -> bool {
+      for (;;) {
+        if (++t_ >= T) {
+          t_ = 0;
+          if (++kb_ >= a.nkb) {
+            kb_ = 0;
+            do {
+              if (++f_ >= C3P_NCELL) return false;
+              act_ = active[f_];
+            } while (!act_);
           }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) mbar_arrive(&a_full[(s + kc) % FT_NAS]);
-        }
-        s += NKC;
-        ++g;
+        if ((act_ >> t_) & 1u) return true;
       }
+    };
+    auto fetch = [&](int f_, int t_, int g_, int rep) -> Slot {
+      Slot d;
+      const int p = (q + g_ * 32) % FT_NQ + rep * FT_NQ;
+      d.p = p < 128 ? p : -1;
+      const int pt = t_ * 128 + (p < 128 ? p : 0);
+      const int off = pre16[pt * 28 + f_];
+      d.n = p < 128 ? (int)pre16[pt * 28 + f_ + 1] - off : 0;
+      d.lb = beg[pt] + (uint32_t)off;
+      const uint32_t at = d.n > 0 ? d.lb + (uint32_t)min(l8, d.n - 1) : 0u;
+      d.ids = __ldg(a.rows + at);
+      d.w = 1.f;
+      if (WEIGHTED) d.w = __ldg(a.weights + at);
+      return d;
+    };
+    auto load4 = [&](float4 (&v)[4][NKC], float (&wv)[4], int ids, float w, int m0, int n, int col) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int id = __shfl_sync(C3P_FULL_MASK, ids, (m0 + m) & 7, 8);
+        wv[m] = WEIGHTED ? __shfl_sync(C3P_FULL_MASK, w, (m0 + m) & 7, 8) : 1.f;
+        const float* src = a.src + (size_t)id * a.Csrc + col + l8 * 4;
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc)
+          v[m][kc] = (m0 + m < n) ? ldg_f4(src + kc * PANEL_K) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto add4 = [&](float4 (&acc)[NKC], const float4 (&v)[4][NKC], const float (&wv)[4]) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+          if (WEIGHTED) {
+            acc[kc].x = fmaf(wv[m], v[m][kc].x, acc[kc].x); acc[kc].y = fmaf(wv[m], v[m][kc].y, acc[kc].y);
+            acc[kc].z = fmaf(wv[m], v[m][kc].z, acc[kc].z); acc[kc].w = fmaf(wv[m], v[m][kc].w, acc[kc].w);
+          } else {
+            acc[kc].x += v[m][kc].x; acc[kc].y += v[m][kc].y;
+            acc[kc].z += v[m][kc].z; acc[kc].w += v[m][kc].w;
+          }
+        }
+    };
+    // gather one slot: acc = (weighted) sum over the cell's members, then the mean
+    auto gather = [&](const Slot& d, int col, float4 (&acc)[NKC]) {
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) acc[kc] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int nmax = max(d.n, __shfl_xor_sync(C3P_FULL_MASK, d.n, 8));
+      nmax = max(nmax, __shfl_xor_sync(C3P_FULL_MASK, nmax, 16));
+      if (nmax > 0) {
+        float4 v0[4][NKC];
+        float w0[4];
+        load4(v0, w0, d.ids, d.w, 0, d.n, col);
+        add4(acc, v0, w0);
+        if (nmax > 4) {
+          load4(v0, w0, d.ids, d.w, 4, d.n, col);
+          add4(acc, v0, w0);
+        }
+        for (int m0 = 8; m0 < nmax; m0 += 8) {   // long lists: further rounds of eight
+          const uint32_t at = d.lb + (uint32_t)min(m0 + l8, max(d.n, 1) - 1);
+          const int idr = __ldg(a.rows + at);
+          float wr = 1.f;
+          if (WEIGHTED) wr = __ldg(a.weights + at);
+          load4(v0, w0, idr, wr, m0, d.n, col);
+          add4(acc, v0, w0);
+          if (m0 + 4 < nmax) {
+            load4(v0, w0, idr, wr, m0 + 4, d.n, col);
+            add4(acc, v0, w0);
+          }
+        }
+        if (!WEIGHTED && d.n > 1) {
+          const float inv = __fdiv_rn(1.f, (float)d.n);   // one divide per cell, not one per channel
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) {
+            acc[kc].x *= inv; acc[kc].y *= inv; acc[kc].z *= inv; acc[kc].w *= inv;
+          }
+        }
+      }
+    };
+    auto store = [&](const Slot& d, int s, const float4 (&acc)[NKC]) {
+      if (d.p >= 0) {
+        const uint32_t o = panel_chunk_offset(d.p, l8);
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc)
+          store_split(a_base + (size_t)((s + kc) % FT_NAS) * FT_A_STAGE + o, 128 * PANEL_ROW_BYTES, acc[kc]);
+      }
+    };
+    const bool two_reps = FT_NQ < 128;
+    int g = 0, s = 0;
+    bool have = advance(gf, gkb, gt, gact);
+    Slot d0;
+    if (have) d0 = fetch(gf, gt, g, 0);
+    unsigned long long ph[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long tc0 = clock64();
+#define C3P_PHASE(i) do { if (a.debug & 32) { long long _t = clock64(); ph[i] += (unsigned long long)(_t - tc0); tc0 = _t; } } while (0)
+    while (have) {
+      const int col = gkb * NKC * PANEL_K;
+      Slot d1;
+      if (two_reps) d1 = fetch(gf, gt, g, 1);       // ids of the second row, behind nothing yet
+      float4 acc[NKC];
+      C3P_PHASE(0);
+      gather(d0, col, acc);
+      C3P_PHASE(1);
+      // ring slots of this group must have been drained by the tensor core
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) {
+        const int st = s + kc, use = st / FT_NAS;
+        if (use >= 1) mbar_wait(&a_empty[st - use * FT_NAS], (uint32_t)((use - 1) & 1));
+      }
+      C3P_PHASE(2);
+      store(d0, s, acc);
+      C3P_PHASE(3);
+      // next group's first row: fetch its ids now, they arrive while the second row is gathered
+      int nf = gf, nkb = gkb, nt = gt;
+      unsigned nact = gact;
+      const bool have_next = advance(nf, nkb, nt, nact);
+      Slot dn;
+      if (have_next) dn = fetch(nf, nt, g + 1, 0);
+      C3P_PHASE(4);
+      if (two_reps && __any_sync(C3P_FULL_MASK, d1.p >= 0)) {
+        gather(d1, col, acc);
+        store(d1, s, acc);
+      }
+      C3P_PHASE(5);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) mbar_arrive(&a_full[(s + kc) % FT_NAS]);
+      }
+      s += NKC;
+      ++g;
+      gf = nf; gkb = nkb; gt = nt; gact = nact;
+      have = have_next;
+      d0 = dn;
+      C3P_PHASE(6);
     }
+    if ((a.debug & 32) && warp == 0 && lane == 0)
+      for (int i = 0; i < 7; ++i) atomicAdd(&g_phase_cycles[i], ph[i]);
     // =========================== epilogue: TMEM -> registers -> global ==============================
     mbar_wait(&acc_full, 0);
     tc_fence_after_sync();
@@ -413,6 +481,7 @@ int launch_prep_weight_panels(const float* filter, void* wp, int Cin, int Cout, 
 static int launch_gather_mma(FTArgs& a, const FTConfig& c, bool weighted, const char* name,
                              cudaStream_t stream) {
   a.nkb = c.nkb; a.T = c.T; a.NWS = c.NWS;
+  a.debug = engine() >= 64 ? (engine() & ~64) : 0;
   const long long tiles = (a.total_points + (long long)a.T * 128 - 1) / ((long long)a.T * 128);
   if (tiles == 0) return CONV3P_OK;
   auto launch = [&](auto kern) -> int {
@@ -463,3 +532,11 @@ int launch_backward_input_tc(const conv3p_geom_t* g, const PlanView& v, const fl
 }
 
 }  // namespace c3p
+
+// profiling helper (tools/engine_timing.py): read and clear the producer phase timers
+extern "C" int conv3p_debug_phase_cycles(unsigned long long* host8) {
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(host8, c3p::g_phase_cycles, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;
+  if (cudaMemcpyToSymbol(c3p::g_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;
+  return CONV3P_OK;
+}

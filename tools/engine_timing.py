@@ -21,3 +21,14 @@ for eng, name in [(0, "auto"), (1, "simt")]:
         e1.record(); torch.cuda.synchronize()
         print(f"{name:10s} {label:7s} {e0.elapsed_time(e1)/5:.3f} ms")
 L.conv3p_set_engine(0)
+
+import ctypes as C
+L.conv3p_set_engine(64 + 32)
+buf = (C.c_ulonglong * 8)()
+L.conv3p_debug_phase_cycles(buf)
+conv3p_forward(plan, pr["input"], pr["filter"]); torch.cuda.synchronize()
+L.conv3p_debug_phase_cycles(buf)
+groups = 683 * 81
+print("forward producer, warp 0, cycles per group:", [round(v / groups) for v in buf[:7]],
+      "= fetch d1 | gather d0 | wait ring | store d0 | advance+fetch next | gather+store d1 | fence+arrive+rotate")
+L.conv3p_set_engine(0)
