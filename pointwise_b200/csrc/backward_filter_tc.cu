@@ -21,7 +21,7 @@ namespace c3p {
 
 using namespace tc;
 
-constexpr int WG_NPW = 20;                    // producer warps (also the epilogue)
+constexpr int WG_NPW = 16;                    // producer warps (also the epilogue): 64 quarter-warps
 constexpr int WG_NQ = WG_NPW * 4;
 constexpr int WG_THREADS = (WG_NPW + 1) * 32; // + MMA issuer / TMEM allocator warp
 constexpr int WG_PTS = 64;                    // points per stage (contraction length of a stage)
@@ -157,41 +157,53 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_backward_filter_tc(const WGAr
           if (lane == 0) mbar_arrive(&x_full[xb]);
         }
         // ---- one G stage per active cell -----------------------------------------------------------------
-        for (int f = f0; f < f1; ++f) {
-          if (!((mask >> f) & 1u)) continue;
+        // Work item = (point, pair of 32-channel panels); quarter-warp q serves items (q + rot) mod NQ (+ NQ).
+        // Software-pipelined over (cell, repetition) slots of this visit: the list ids of the next slot are
+        // fetched while the rows of the current one are in flight.
+        const int items = WG_PTS * (gp / 2);
+        auto fetch = [&](int f_, int gs_, int rep, int& e_out) -> GatherSlot {
+          const int e = rep * WG_NQ + (q + gs_ * 32) % WG_NQ;
+          const bool valid = e < items;
+          e_out = valid ? e : -1;
+          const int r = valid ? e / (gp / 2) : 0;
+          const int off = pre16[(tb * WG_PTS + r) * 28 + f_];
+          const int n = valid ? (int)pre16[(tb * WG_PTS + r) * 28 + f_ + 1] - off : 0;
+          return fetch_slot<true>(n, beg[tb * WG_PTS + r] + (uint32_t)off, a.rows, a.weights, l8);
+        };
+        const int nrep = (items + WG_NQ - 1) / WG_NQ;
+        unsigned todo = mask;
+        int f = __ffs(todo) - 1;
+        int e_cur = -1;
+        GatherSlot d = fetch(f, gs, 0, e_cur);
+        while (todo) {
+          todo &= todo - 1;
+          const int f_next = todo ? __ffs(todo) - 1 : -1;
           const int slot = gs & 1, use = gs >> 1;
           unsigned char* stage = g_base + (size_t)slot * 2 * g_half;
-          const int items = WG_PTS * (gp / 2);          // (point, pair of panels)
-          const int rot = (gs * 32) % WG_NQ;
-          bool waited = false;
-          // every lane runs the same number of repetitions: the gather uses warp-wide shuffles
-          for (int e0 = 0; e0 < items; e0 += WG_NQ) {
-            const int e = e0 + (q + rot) % WG_NQ;
-            const bool valid = e < items;
-            const int r = valid ? e / (gp / 2) : 0, kb = valid ? e - r * (gp / 2) : 0;
-            int n = 0, off = 0;
-            if (valid) {
-              off = pre16[(tb * WG_PTS + r) * 28 + f];
-              n = (int)pre16[(tb * WG_PTS + r) * 28 + f + 1] - off;
-            }
+          for (int rep = 0; rep < nrep; ++rep) {
+            int e_next = -1;
+            GatherSlot dn;
+            dn.n = 0; dn.lb = 0; dn.ids = 0; dn.w = 0.f;
+            if (rep + 1 < nrep) dn = fetch(f, gs, rep + 1, e_next);
+            else if (f_next >= 0) dn = fetch(f_next, gs + 1, 0, e_next);
+            const int kb = e_cur >= 0 ? e_cur % (gp / 2) : 0, r = e_cur >= 0 ? e_cur / (gp / 2) : 0;
             float4 acc[2];
-            const size_t lbase = valid ? (size_t)beg[tb * WG_PTS + r] + off : 0;
-            gather_rows<2, true>(acc, a.grad_out, Cout, kb * 2 * PANEL_K, a.rows, a.weights, lbase, n, l8);
-            if (!waited) {
-              if (use >= 1) mbar_wait(&g_empty[slot], (uint32_t)((use - 1) & 1));
-              waited = true;
-            }
-            if (valid) {
+            gather_slot<2, true>(acc, d, a.grad_out, Cout, kb * 2 * PANEL_K, a.rows, a.weights, l8);
+            if (rep == 0 && use >= 1) mbar_wait(&g_empty[slot], (uint32_t)((use - 1) & 1));
+            if (e_cur >= 0) {
 #pragma unroll
               for (int kc = 0; kc < 2; ++kc)
                 store_split(stage + (size_t)(kb * 2 + kc) * WG_PANEL + panel_chunk_offset_mn(r, l8), g_half,
                             acc[kc]);
             }
+            d = dn;
+            e_cur = e_next;
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&g_full[slot]);
           ++gs;
+          f = f_next;
         }
         ++visit;
       }

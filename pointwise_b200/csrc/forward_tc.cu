@@ -153,10 +153,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_gather_mma_tc(const FTArgs a)
     const int q = warp * 4 + (lane >> 3);
     const int l8 = lane & 7;
     struct Slot {
-      int p, n;          // row in the sub-tile (or -1), members of its cell
-      uint32_t lb;       // list position
-      int ids;           // lane l8: row id of member l8 (padding lanes: member 0)
-      float w;           // lane l8: weight of member l8
+      int p;          // row in the sub-tile, or -1
+      GatherSlot gs;  // its cell's list: members, position, prefetched ids / weights
     };
     int gf = -1, gkb = a.nkb - 1, gt = T - 1;   // group iterator (cell, K batch, sub-tile)
     unsigned gact = 0;
@@ -181,74 +179,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_gather_mma_tc(const FTArgs a)
       d.p = p < 128 ? p : -1;
       const int pt = t_ * 128 + (p < 128 ? p : 0);
       const int off = pre16[pt * 28 + f_];
-      d.n = p < 128 ? (int)pre16[pt * 28 + f_ + 1] - off : 0;
-      d.lb = beg[pt] + (uint32_t)off;
-      const uint32_t at = d.n > 0 ? d.lb + (uint32_t)min(l8, d.n - 1) : 0u;
-      d.ids = __ldg(a.rows + at);
-      d.w = 1.f;
-      if (WEIGHTED) d.w = __ldg(a.weights + at);
+      const int n = p < 128 ? (int)pre16[pt * 28 + f_ + 1] - off : 0;
+      d.gs = fetch_slot<WEIGHTED>(n, beg[pt] + (uint32_t)off, a.rows, a.weights, l8);
       return d;
     };
-    auto load4 = [&](float4 (&v)[4][NKC], float (&wv)[4], int ids, float w, int m0, int n, int col) {
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int id = __shfl_sync(C3P_FULL_MASK, ids, (m0 + m) & 7, 8);
-        wv[m] = WEIGHTED ? __shfl_sync(C3P_FULL_MASK, w, (m0 + m) & 7, 8) : 1.f;
-        const float* src = a.src + (size_t)id * a.Csrc + col + l8 * 4;
-#pragma unroll
-        for (int kc = 0; kc < NKC; ++kc)
-          v[m][kc] = (m0 + m < n) ? ldg_f4(src + kc * PANEL_K) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto add4 = [&](float4 (&acc)[NKC], const float4 (&v)[4][NKC], const float (&wv)[4]) {
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int kc = 0; kc < NKC; ++kc) {
-          if (WEIGHTED) {
-            acc[kc].x = fmaf(wv[m], v[m][kc].x, acc[kc].x); acc[kc].y = fmaf(wv[m], v[m][kc].y, acc[kc].y);
-            acc[kc].z = fmaf(wv[m], v[m][kc].z, acc[kc].z); acc[kc].w = fmaf(wv[m], v[m][kc].w, acc[kc].w);
-          } else {
-            acc[kc].x += v[m][kc].x; acc[kc].y += v[m][kc].y;
-            acc[kc].z += v[m][kc].z; acc[kc].w += v[m][kc].w;
-          }
-        }
-    };
-    // gather one slot: acc = (weighted) sum over the cell's members, then the mean
     auto gather = [&](const Slot& d, int col, float4 (&acc)[NKC]) {
-#pragma unroll
-      for (int kc = 0; kc < NKC; ++kc) acc[kc] = make_float4(0.f, 0.f, 0.f, 0.f);
-      int nmax = max(d.n, __shfl_xor_sync(C3P_FULL_MASK, d.n, 8));
-      nmax = max(nmax, __shfl_xor_sync(C3P_FULL_MASK, nmax, 16));
-      if (nmax > 0) {
-        float4 v0[4][NKC];
-        float w0[4];
-        load4(v0, w0, d.ids, d.w, 0, d.n, col);
-        add4(acc, v0, w0);
-        if (nmax > 4) {
-          load4(v0, w0, d.ids, d.w, 4, d.n, col);
-          add4(acc, v0, w0);
-        }
-        for (int m0 = 8; m0 < nmax; m0 += 8) {   // long lists: further rounds of eight
-          const uint32_t at = d.lb + (uint32_t)min(m0 + l8, max(d.n, 1) - 1);
-          const int idr = __ldg(a.rows + at);
-          float wr = 1.f;
-          if (WEIGHTED) wr = __ldg(a.weights + at);
-          load4(v0, w0, idr, wr, m0, d.n, col);
-          add4(acc, v0, w0);
-          if (m0 + 4 < nmax) {
-            load4(v0, w0, idr, wr, m0 + 4, d.n, col);
-            add4(acc, v0, w0);
-          }
-        }
-        if (!WEIGHTED && d.n > 1) {
-          const float inv = __fdiv_rn(1.f, (float)d.n);   // one divide per cell, not one per channel
-#pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) {
-            acc[kc].x *= inv; acc[kc].y *= inv; acc[kc].z *= inv; acc[kc].w *= inv;
-          }
-        }
-      }
+      gather_slot<NKC, WEIGHTED>(acc, d.gs, a.src, a.Csrc, col, a.rows, a.weights, l8);
     };
     auto store = [&](const Slot& d, int s, const float4 (&acc)[NKC]) {
       if (d.p >= 0) {
