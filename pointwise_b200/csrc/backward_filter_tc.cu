@@ -66,7 +66,8 @@ __global__ void k_tile_masks(const int* __restrict__ cnt, const long long* __res
 __global__ void __launch_bounds__(WG_THREADS, 1) k_backward_filter_tc(const WGArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Cin = a.Cin, Cout = a.Cout, FG = a.FG;
-  const int gp = Cout / 32, xp = Cin / 32;              // panels per operand
+  constexpr int gp = 4;                                 // Cout == 128: four 32-channel panels of G
+  const int xp = Cin / 32;                              // panels of the input rows
   const uint32_t g_half = (uint32_t)gp * WG_PANEL;      // hi (or lo) part of a G stage
   const uint32_t x_half = (uint32_t)xp * WG_PANEL;
   unsigned char* g_base = smem;                          // 2 stages x (hi, lo)

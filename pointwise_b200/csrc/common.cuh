@@ -126,6 +126,23 @@ __device__ __forceinline__ int tap_of(float v, float lo, float voxel, int full, 
   return (t * stride == c) ? t : -1;
 }
 
+// Same result, cheaper on average: the voxel index is first formed with a reciprocal multiply; only when that
+// quotient lies within a guard band of an integer (where it could truncate differently from the IEEE
+// quotient: |q_approx - q_ieee| <= 1.8e-7 * q) is the exact division evaluated.  Bit-identical to tap_of.
+__device__ __forceinline__ int tap_of_fast(float v, float lo, float voxel, float inv_voxel, int full,
+                                           int stride) {
+  const float d = __fsub_rn(v, lo);
+  const float qa = d * inv_voxel;
+  int c = __float2int_rz(qa);
+  const float fr = qa - (float)c;
+  const float guard = 1e-4f + fabsf(qa) * 1e-6f;
+  if (!(qa >= 0.f) || fr < guard || fr > 1.f - guard) c = __float2int_rz(__fdiv_rn(d, voxel));
+  c = min(c, full - 1);
+  if (c < 0) return -1;
+  int t = c / stride;
+  return (t * stride == c) ? t : -1;
+}
+
 // Uniform-grid coordinate of v: (int)((v - vmin) / cell) -- tf_conv3p_atrous.cpp:192-194.  Monotone
 // non-decreasing in v, which is all the candidate windows rely on.
 __device__ __forceinline__ int grid_coord(float v, float vmin, float cell, int dim) {

@@ -78,7 +78,7 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* __restrict__ keys
 struct Query {
   float lo[3], hi[3];
   int full[3], stride[3];
-  float voxel;
+  float voxel, inv_voxel;
   AxisWin wx, wy, wz;
   int dimx, dimy;
 };
@@ -94,10 +94,14 @@ __device__ __forceinline__ void sweep(const Query& q, const uint32_t* __restrict
     const int e = s0 + lane;
     int start = 0, len = 0;
     if (e < nseg) {
-      const int xr = e % q.wx.n;
-      const int r = e / q.wx.n;
-      const int cy = window_cell(q.wy, r % q.wy.cells);
-      const int cz = window_cell(q.wz, r / q.wy.cells);
+      int xr = 0, r = e;
+      if (q.wx.n > 1) {  // dilated windows only: up to three x ranges per row
+        r = e / q.wx.n;
+        xr = e - r * q.wx.n;
+      }
+      const int rz = r / q.wy.cells;
+      const int cy = window_cell(q.wy, r - rz * q.wy.cells);
+      const int cz = window_cell(q.wz, rz);
       const uint32_t rowkey = (uint32_t)((cz * q.dimy + cy) * q.dimx);
       start = lower_bound_key(keys, N, rowkey + (uint32_t)q.wx.lo[xr]);
       len = lower_bound_key(keys, N, rowkey + (uint32_t)q.wx.hi[xr] + 1u) - start;
@@ -153,8 +157,12 @@ __device__ __forceinline__ int place(bool valid, int f, int* pre, int* run) {
   return slot;
 }
 
+// S = compile-time isotropic stride 1..4 (every reference layer: the tap arithmetic then has no runtime
+// integer division), 0 = per-axis runtime strides.
+template <int S>
 __global__ void __launch_bounds__(NB_THREADS)
-k_neighbor_search(int B, int N, int sx, int sy, int sz, float voxel, long long capacity, PlanView v) {
+k_neighbor_search(int B, int N, int sx_, int sy_, int sz_, float voxel, long long capacity, PlanView v) {
+  const int sx = S ? S : sx_, sy = S ? S : sy_, sz = S ? S : sz_;
   __shared__ uint32_t stash[NB_WARPS][STASH_CAP];
   __shared__ int wcnt[NB_WARPS][32];
   __shared__ int wpre[NB_WARPS][32];
@@ -174,6 +182,7 @@ k_neighbor_search(int B, int N, int sx, int sy, int sz, float voxel, long long c
 
   Query q;
   q.voxel = voxel;
+  q.inv_voxel = __fdiv_rn(1.0f, voxel);
   q.stride[0] = sx; q.stride[1] = sy; q.stride[2] = sz;
   const float centre[3] = {me.x, me.y, me.z};
 #pragma unroll
@@ -251,9 +260,11 @@ k_neighbor_search(int B, int N, int sx, int sy, int sz, float voxel, long long c
 // Backward lists: for j and every ii in N(j) (j's forward list), the cell of j in ii's frame with NO
 // box test; dropped if it is a hole or count(ii, f') == 0 -- tf_conv3p_atrous.cpp:654-679.  Stored at
 // the same offsets as the forward lists (a backward list is never longer), grouped by f'.
+template <int S>
 __global__ void __launch_bounds__(NB_THREADS)
-k_backward_lists(int B, int N, int sx, int sy, int sz, float voxel, long long capacity,
+k_backward_lists(int B, int N, int sx_, int sy_, int sz_, float voxel, long long capacity,
                  const float* __restrict__ points, PlanView v) {
+  const int sx = S ? S : sx_, sy = S ? S : sy_, sz = S ? S : sz_;
   __shared__ int wcnt[NB_WARPS][32];
   __shared__ int wpre[NB_WARPS][32];
   __shared__ int wrun[NB_WARPS][32];
@@ -276,15 +287,16 @@ k_backward_lists(int B, int N, int sx, int sy, int sz, float voxel, long long ca
     return;
   }
   const int full[3] = {2 * sx + 1, 2 * sy + 1, 2 * sz + 1};
+  const float inv_voxel = __fdiv_rn(1.0f, voxel);
   const int* fwd = v.pair_row + begin;
 
   auto rebin = [&](int m, int& ii, int& members) -> int {
     ii = __ldg(fwd + m);
     const float kx = __ldg(points + 3 * (size_t)ii), ky = __ldg(points + 3 * (size_t)ii + 1),
                 kz = __ldg(points + 3 * (size_t)ii + 2);
-    int tx = tap_of(me.x, box_lo(kx, full[0], voxel), voxel, full[0], sx);  // :658-669
-    int ty = tap_of(me.y, box_lo(ky, full[1], voxel), voxel, full[1], sy);
-    int tz = tap_of(me.z, box_lo(kz, full[2], voxel), voxel, full[2], sz);
+    int tx = tap_of_fast(me.x, box_lo(kx, full[0], voxel), voxel, inv_voxel, full[0], sx);  // :658-669
+    int ty = tap_of_fast(me.y, box_lo(ky, full[1], voxel), voxel, inv_voxel, full[1], sy);
+    int tz = tap_of_fast(me.z, box_lo(kz, full[2], voxel), voxel, inv_voxel, full[2], sz);
     if ((tx | ty | tz) < 0) return -1;                                      // :672
     const int f = (tz * 3 + ty) * 3 + tx;                                   // :677
     members = __ldg(v.count_table + (size_t)ii * C3P_NCELL + f);
@@ -329,8 +341,12 @@ int launch_neighbor_search(const conv3p_geom_t* g, const PlanView& v, cudaStream
   const unsigned grid = (unsigned)((pts + NB_WARPS - 1) / NB_WARPS);
   {
     LaunchTimer timer_("k_neighbor_search", stream);
-    k_neighbor_search<<<grid, NB_THREADS, 0, stream>>>(g->B, g->N, g->stride[0], g->stride[1],
-                                                     g->stride[2], g->voxel_size, g->pair_capacity, v);
+    const int iso = (g->stride[0] == g->stride[1] && g->stride[1] == g->stride[2] && g->stride[0] <= 4)
+                        ? g->stride[0] : 0;
+    auto kern = iso == 1 ? k_neighbor_search<1> : iso == 2 ? k_neighbor_search<2>
+              : iso == 3 ? k_neighbor_search<3> : iso == 4 ? k_neighbor_search<4> : k_neighbor_search<0>;
+    kern<<<grid, NB_THREADS, 0, stream>>>(g->B, g->N, g->stride[0], g->stride[1], g->stride[2],
+                                          g->voxel_size, g->pair_capacity, v);
   }
   C3P_LAUNCH_CHECK("k_neighbor_search");
   return CONV3P_OK;
@@ -344,9 +360,12 @@ int launch_backward_lists(const conv3p_geom_t* g, const float* points, const Pla
     const unsigned grid = (unsigned)((pts + NB_WARPS - 1) / NB_WARPS);
     {
     LaunchTimer timer_("k_backward_lists", stream);
-    k_backward_lists<<<grid, NB_THREADS, 0, stream>>>(g->B, g->N, g->stride[0], g->stride[1],
-                                                      g->stride[2], g->voxel_size, g->pair_capacity,
-                                                      points, v);
+    const int iso = (g->stride[0] == g->stride[1] && g->stride[1] == g->stride[2] && g->stride[0] <= 4)
+                        ? g->stride[0] : 0;
+    auto kern = iso == 1 ? k_backward_lists<1> : iso == 2 ? k_backward_lists<2>
+              : iso == 3 ? k_backward_lists<3> : iso == 4 ? k_backward_lists<4> : k_backward_lists<0>;
+    kern<<<grid, NB_THREADS, 0, stream>>>(g->B, g->N, g->stride[0], g->stride[1], g->stride[2],
+                                          g->voxel_size, g->pair_capacity, points, v);
   }
     C3P_LAUNCH_CHECK("k_backward_lists");
   }
