@@ -201,11 +201,14 @@ def algorithmic_bytes(kernel: str, pts: int, Cin: int, Cout: int, kbar: float, k
         "k_backward_input_tc": kbar_b * (4 * Cout + 8) + 27 * 4 + 8 + 16 + 4 * Cin,
         "k_backward_filter": kbar_b * (4 * Cout + 8) + 27 * 4 + 8 + 16 + 4 * Cin,
         "k_backward_filter_tc": kbar_b * (4 * Cout + 8) + 27 * 4 + 8 + 16 + 4 * Cin,
+        "k_small_forward": kbar * (4 * Cin + 4) + 27 * 4 + 8 + 16 + 4 * Cout,
+        "k_small_backward_input": kbar_b * (4 * Cout + 8) + 27 * 4 + 8 + 16 + 4 * Cin,
+        "k_small_backward_filter": kbar_b * (4 * Cout + 8) + 27 * 4 + 8 + 16 + 4 * Cin,
         "k_neighbor_search": 16 + 27 * 4 + 12 + kbar * 4 + 2.4 * kbar * 16,
         "k_backward_lists": 16 + kbar * (4 + 12 + 4) + 27 * 4 + kbar_b * 8,
         "k_cloud_sort": 12 + 16 + 4 + 4 * 16,
     }.get(kernel, 0.0)
-    fixed = nW if kernel.startswith("k_gather") or kernel.endswith("_tc") else (2 * nW if kernel.startswith("k_backward_filter") else 0)
+    fixed = nW if kernel.startswith("k_gather") or kernel.endswith("_tc") or kernel.startswith("k_small_") else (2 * nW if kernel.startswith("k_backward_filter") else 0)
     return per_point * pts + fixed
 
 

@@ -161,8 +161,9 @@ const char* conv3p_last_cuda_error(void); /* thread-local text of the last CONV3
 int conv3p_abi_version(void);
 /* Number of kernels this library launched on behalf of the calling thread since the last reset. */
 long long conv3p_launch_count(int reset);
-/* Selects the contraction engine: 0 = auto, 1 = fp32 SIMT only, 2 = tensor cores (3xTF32) where
- * supported.  Returns the previous value.  Process-wide. */
+/* Selects the contraction engine: 0 = auto, 1 = fp32 SIMT only (tile engine or warp-per-point engine by
+ * channel count), 2 = tensor cores (3xTF32) where supported, 3 = generic fp32 tile engine only.  Values
+ * >= 64 carry profiling/ablation bits (tools/engine_timing.py).  Returns the previous value.  Process-wide. */
 int conv3p_set_engine(int engine);
 
 /* Per-kernel timing for benchmarks: while enabled, every kernel launch is bracketed by CUDA events

@@ -259,6 +259,10 @@ size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
   if (check_geom(geom) || check_channels(Cin, Cout)) return 0;
   // [weight panel images | split-K partials of grad_filter]
   size_t filt = backward_filter_scratch_bytes(geom, Cin, Cout);
+  if (small_backward_filter_supported(Cin, Cout)) {
+    const size_t t = backward_filter_small_scratch_bytes(Cin, Cout);
+    if (t > filt) filt = t;
+  }
   if (backward_filter_tc_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
     const size_t t = backward_filter_tc_scratch_bytes(geom, Cin, Cout);
     if (t > filt) filt = t;
@@ -280,6 +284,8 @@ int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float*
     if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
     return launch_forward_tc(geom, v, input, filter, Cin, Cout, output, scratch, scratch_bytes, stream);
   }
+  if (engine() != 3 && small_channels_supported(Cin, Cout))
+    return launch_forward_small(geom, v, input, filter, Cin, Cout, output, stream);
   return launch_forward_simt(geom, v, input, filter, Cin, Cout, output, stream);
 }
 
@@ -299,6 +305,8 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
       if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
       st = launch_backward_input_tc(geom, v, grad_output, filter, Cin, Cout, grad_input, scratch,
                                     scratch_bytes, stream);
+    } else if (engine() != 3 && small_channels_supported(Cin, Cout)) {
+      st = launch_backward_input_small(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);
     } else {
       st = launch_backward_input_simt(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);
     }
@@ -311,6 +319,9 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
     if (engine() != 1 && backward_filter_tc_supported(geom->N, geom->pair_capacity, Cin, Cout))
       st = launch_backward_filter_tc(geom, v, grad_output, input, Cin, Cout, grad_filter,
                                      static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);
+    else if (engine() != 3 && small_backward_filter_supported(Cin, Cout))
+      st = launch_backward_filter_small(geom, v, grad_output, input, Cin, Cout, grad_filter,
+                                        static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);
     else
       st = launch_backward_filter_simt(geom, v, grad_output, input, Cin, Cout, grad_filter,
                                        static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);

@@ -82,6 +82,18 @@ int launch_backward_filter_tc(const conv3p_geom_t* g, const PlanView& v, const f
                               const float* input, int Cin, int Cout, float* grad_filter, void* scratch,
                               size_t scratch_bytes, cudaStream_t stream);
 
+// warp-per-point fp32 engine for the reference models' small channel counts (3, 9, 13, 36)
+bool small_channels_supported(int Cin, int Cout);
+bool small_backward_filter_supported(int Cin, int Cout);
+size_t backward_filter_small_scratch_bytes(int Cin, int Cout);
+int launch_forward_small(const conv3p_geom_t* g, const PlanView& v, const float* input, const float* filter,
+                         int Cin, int Cout, float* output, cudaStream_t stream);
+int launch_backward_input_small(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
+                                const float* filter, int Cin, int Cout, float* grad_input, cudaStream_t stream);
+int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
+                                 const float* input, int Cin, int Cout, float* grad_filter, void* scratch,
+                                 size_t scratch_bytes, cudaStream_t stream);
+
 }  // namespace c3p
 
 #define C3P_CUDA(expr)                                        \

@@ -369,8 +369,6 @@ int launch_backward_lists(const conv3p_geom_t* g, const float* points, const Pla
   }
     C3P_LAUNCH_CHECK("k_backward_lists");
   }
-  const long long one = 1;
-  (void)one;
   return CONV3P_OK;
 }
 

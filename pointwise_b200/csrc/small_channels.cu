@@ -1,0 +1,299 @@
+// small_channels.cu -- fp32 SIMT engine for the reference models' own layer shapes (3->9, 9->9, 36->13:
+// pointcnn2_acsd.py:48-67, scene_seg/pointcnn_scene_seg_acsd.py:51-57), where a cell's weight matrix is far
+// too small for an MMA tile.  One warp per point (voxel-sorted order), the whole filter resident in shared
+// memory, persistent CTAs:
+//
+//   forward / grad_input : for every non-empty cell of the point, lanes = channels gather the cell's rows
+//                          (mean, or weighted sum over the backward list) and lanes = outputs accumulate
+//                          out[n] += sum_k A[k] * W_f[k, n]   (tf_conv3p_atrous.cpp:480-494 / :682-692)
+//   grad_filter          : the gathered G_f[j, :] is multiplied with input[j, :] and added into a per-warp-
+//                          private copy of grad_filter in shared memory (no atomics, fixed order); the
+//                          copies and then the CTA partials are reduced in a fixed order
+//                          (tf_conv3p_atrous.cpp:694-716).  Used when 8 copies fit in shared memory.
+#include "common.cuh"
+
+namespace c3p {
+
+constexpr int SC_WARPS = 8;
+constexpr int SC_THREADS = SC_WARPS * 32;
+constexpr int SC_MAXC = 64;  // widest channel count served (two values per lane)
+
+struct SCArgs {
+  const float* src;        // gathered rows [B*N, Csrc]
+  const float* filter;     // [27, Cin, Cout]
+  float* out;              // [B*N, Nout]
+  const int* cnt;          // [B*N, 27]
+  const long long* begin;
+  const int* len;
+  const int* rows;
+  const float* weights;    // nullptr: per-cell mean
+  const float4* sorted_xyzi;
+  long long total_points, capacity;
+  int N, Cin, Cout, Csrc, Nout;
+  int transposed;          // 0: B[k][n] = W[f][k][n]; 1: B[k][n] = W[f][n][k]
+};
+
+// out[p, n] = sum_f sum_k A_f[p, k] * B_f[k, n]
+__global__ void __launch_bounds__(SC_THREADS) k_small_gather_contract(const SCArgs a) {
+  extern __shared__ float sc_w[];  // [27][Csrc][Nout] (B_f, contraction index major)
+  const int Csrc = a.Csrc, Nout = a.Nout;
+  for (int e = threadIdx.x; e < C3P_NCELL * Csrc * Nout; e += SC_THREADS) {
+    const int n = e % Nout, k = (e / Nout) % Csrc, f = e / (Nout * Csrc);
+    sc_w[e] = a.transposed ? a.filter[((size_t)f * a.Cin + n) * a.Cout + k]
+                           : a.filter[((size_t)f * a.Cin + k) * a.Cout + n];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long stride = (long long)gridDim.x * SC_WARPS;
+  for (long long s = (long long)blockIdx.x * SC_WARPS + warp; s < a.total_points; s += stride) {
+    const int b = (int)(s / a.N);
+    const int row = b * a.N + __float_as_int(a.sorted_xyzi[s].w);
+    const long long bg = a.begin[row];
+    const bool ok = bg + a.len[row] <= a.capacity;
+    const int mine = (ok && lane < C3P_NCELL) ? __ldg(a.cnt + (size_t)row * C3P_NCELL + lane) : 0;
+    float acc0 = 0.f, acc1 = 0.f;  // outputs n = lane, lane + 32
+    long long at = bg;
+    int excl = mine;               // list position of cell f = exclusive prefix of the counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(C3P_FULL_MASK, excl, o);
+      if (lane >= o) excl += u;
+    }
+    excl -= mine;
+    unsigned cells = __ballot_sync(C3P_FULL_MASK, mine > 0);
+    while (cells) {
+      const int f = __ffs(cells) - 1;
+      cells &= cells - 1;
+      const int before = __shfl_sync(C3P_FULL_MASK, excl, f);
+      const int n = __shfl_sync(C3P_FULL_MASK, mine, f);
+      const int* r = a.rows + at + before;
+      float a0 = 0.f, a1 = 0.f;  // aggregate channels k = lane, lane + 32
+      int m = 0;
+      for (; m + 2 <= n; m += 2) {  // two members in flight
+        const int j0 = __ldg(r + m), j1 = __ldg(r + m + 1);
+        const float w0 = a.weights ? __ldg(a.weights + at + before + m) : 1.f;
+        const float w1 = a.weights ? __ldg(a.weights + at + before + m + 1) : 1.f;
+        const float* p0 = a.src + (size_t)j0 * Csrc;
+        const float* p1 = a.src + (size_t)j1 * Csrc;
+        const float x00 = lane < Csrc ? __ldg(p0 + lane) : 0.f, x10 = lane < Csrc ? __ldg(p1 + lane) : 0.f;
+        const float x01 = lane + 32 < Csrc ? __ldg(p0 + lane + 32) : 0.f;
+        const float x11 = lane + 32 < Csrc ? __ldg(p1 + lane + 32) : 0.f;
+        a0 = fmaf(w0, x00, a0); a0 = fmaf(w1, x10, a0);
+        a1 = fmaf(w0, x01, a1); a1 = fmaf(w1, x11, a1);
+      }
+      if (m < n) {
+        const int j0 = __ldg(r + m);
+        const float w0 = a.weights ? __ldg(a.weights + at + before + m) : 1.f;
+        const float* p0 = a.src + (size_t)j0 * Csrc;
+        a0 = fmaf(w0, lane < Csrc ? __ldg(p0 + lane) : 0.f, a0);
+        a1 = fmaf(w0, lane + 32 < Csrc ? __ldg(p0 + lane + 32) : 0.f, a1);
+      }
+      if (!a.weights && n > 1) {
+        const float inv = __fdiv_rn(1.f, (float)n);
+        a0 *= inv;
+        a1 *= inv;
+      }
+      const float* wf = sc_w + (size_t)f * Csrc * Nout;
+      for (int k = 0; k < Csrc; ++k) {
+        const float ak = __shfl_sync(C3P_FULL_MASK, k < 32 ? a0 : a1, k & 31);
+        if (lane < Nout) acc0 = fmaf(ak, wf[k * Nout + lane], acc0);
+        if (lane + 32 < Nout) acc1 = fmaf(ak, wf[k * Nout + lane + 32], acc1);
+      }
+    }
+    const float nanv = __int_as_float(0x7fc00000);
+    if (lane < Nout) a.out[(size_t)row * Nout + lane] = ok ? acc0 : nanv;
+    if (lane + 32 < Nout) a.out[(size_t)row * Nout + lane + 32] = ok ? acc1 : nanv;
+  }
+}
+
+struct SFArgs {
+  const float* grad_out;
+  const float* input;
+  const int* cnt;
+  const long long* begin;
+  const int* len;
+  const int* rows;
+  const float* weights;
+  const float4* sorted_xyzi;
+  float* partial;  // [gridDim.x][27*Cin*Cout]
+  long long total_points, capacity;
+  int N, Cin, Cout;
+};
+
+__global__ void __launch_bounds__(SC_THREADS) k_small_backward_filter(const SFArgs a) {
+  extern __shared__ float sf_gw[];  // [warps][27][Cin][Cout]: one private copy per warp
+  const int Cin = a.Cin, Cout = a.Cout;
+  const int nW = C3P_NCELL * Cin * Cout;
+  const int copies = SC_WARPS;
+  for (int e = threadIdx.x; e < copies * nW; e += SC_THREADS) sf_gw[e] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* gw = sf_gw + (size_t)warp * nW;
+  const int slots = Cout <= 32 ? 32 / Cout : 1;
+  const int slot = Cout <= 32 ? lane / Cout : 0, kk = Cout <= 32 ? lane - slot * Cout : lane;
+  const bool slot_ok = slot < slots;
+  const long long stride = (long long)gridDim.x * SC_WARPS;
+  for (long long s = (long long)blockIdx.x * SC_WARPS + warp; s < a.total_points; s += stride) {
+    const int b = (int)(s / a.N);
+    const int row = b * a.N + __float_as_int(a.sorted_xyzi[s].w);
+    const long long bg = a.begin[row];
+    if (bg + a.len[row] > a.capacity) continue;
+    const int mine = lane < C3P_NCELL ? __ldg(a.cnt + (size_t)row * C3P_NCELL + lane) : 0;
+    const float x0 = lane < Cin ? __ldg(a.input + (size_t)row * Cin + lane) : 0.f;
+    const float x1 = lane + 32 < Cin ? __ldg(a.input + (size_t)row * Cin + lane + 32) : 0.f;
+    int excl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(C3P_FULL_MASK, excl, o);
+      if (lane >= o) excl += u;
+    }
+    excl -= mine;
+    unsigned cells = __ballot_sync(C3P_FULL_MASK, mine > 0);
+    while (cells) {
+      const int f = __ffs(cells) - 1;
+      cells &= cells - 1;
+      const int before = __shfl_sync(C3P_FULL_MASK, excl, f);
+      const int n = __shfl_sync(C3P_FULL_MASK, mine, f);
+      float g0 = 0.f, g1 = 0.f;  // G_f[j, c], c = lane, lane + 32 (after the slot reduction)
+      const int* r = a.rows + bg + before;
+      const float* wl = a.weights + bg + before;
+      for (int m = 0; m < n; m += 2 * slots) {
+        const int m0 = m + slot, m1 = m + slots + slot;
+        const bool v0 = slot_ok && m0 < n, v1 = slot_ok && m1 < n;
+        const int j0 = v0 ? __ldg(r + m0) : 0, j1 = v1 ? __ldg(r + m1) : 0;
+        const float w0 = v0 ? __ldg(wl + m0) : 0.f, w1 = v1 ? __ldg(wl + m1) : 0.f;
+        const float* p0 = a.grad_out + (size_t)j0 * Cout;
+        const float* p1 = a.grad_out + (size_t)j1 * Cout;
+        g0 = fmaf(w0, v0 ? __ldg(p0 + kk) : 0.f, g0);
+        g0 = fmaf(w1, v1 ? __ldg(p1 + kk) : 0.f, g0);
+        if (Cout > 32) {
+          g1 = fmaf(w0, (v0 && lane + 32 < Cout) ? __ldg(p0 + lane + 32) : 0.f, g1);
+          g1 = fmaf(w1, (v1 && lane + 32 < Cout) ? __ldg(p1 + lane + 32) : 0.f, g1);
+        }
+      }
+      for (int sl = 1; sl < slots; ++sl) {
+        const float o = __shfl_sync(C3P_FULL_MASK, g0, (lane + sl * Cout) & 31);
+        if (lane < Cout) g0 += o;
+      }
+      float* gf = gw + (size_t)f * Cin * Cout;
+      for (int k = 0; k < Cin; ++k) {
+        const float xk = __shfl_sync(C3P_FULL_MASK, k < 32 ? x0 : x1, k & 31);
+        // the warp owns this copy: plain read-modify-write, fixed order
+        if (lane < Cout) gf[k * Cout + lane] = fmaf(xk, g0, gf[k * Cout + lane]);
+        if (lane + 32 < Cout) gf[k * Cout + lane + 32] = fmaf(xk, g1, gf[k * Cout + lane + 32]);
+      }
+    }
+  }
+  __syncthreads();
+  float* dst = a.partial + (size_t)blockIdx.x * nW;
+  for (int e = threadIdx.x; e < nW; e += SC_THREADS) {
+    float sum = 0.f;
+    for (int c = 0; c < copies; ++c) sum += sf_gw[(size_t)c * nW + e];  // fixed order over the warps
+    dst[e] = sum;
+  }
+}
+
+__global__ void k_small_reduce(const float* __restrict__ partial, int S, int nW, float* __restrict__ out) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nW) return;
+  float s = 0.f;
+  for (int i = 0; i < S; ++i) s += partial[(size_t)i * nW + w];
+  out[w] = s;
+}
+
+static int sc_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  (void)cudaGetLastError();
+  return sms < 1 ? 148 : sms;
+}
+
+// Measured on B200 (profiles/r1_summary.md): the warp-per-point gather-contract wins up to ~16 channels (2x at
+// ModelNet40 densities), the tile engine from 36->13 up; the private-copy grad_filter kernel wins whenever it fits.
+bool small_channels_supported(int Cin, int Cout) {
+  return Cin <= 16 && Cout <= 16;
+}
+bool small_backward_filter_supported(int Cin, int Cout) {
+  return Cin <= 40 && Cout <= 40 && (size_t)SC_WARPS * C3P_NCELL * Cin * Cout * 4 <= 96 * 1024;
+}
+
+static int launch_small_gc(SCArgs& a, const char* name, cudaStream_t stream) {
+  if (a.total_points == 0) return CONV3P_OK;
+  const size_t smem = sizeof(float) * C3P_NCELL * a.Csrc * a.Nout;
+  if (smem > 48 * 1024)
+    C3P_CUDA(cudaFuncSetAttribute(k_small_gather_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
+  long long grid = (long long)sc_sms() * per_sm;
+  const long long need = (a.total_points + SC_WARPS - 1) / SC_WARPS;
+  if (grid > need) grid = need;
+  {
+    LaunchTimer timer_(name, stream);
+    k_small_gather_contract<<<(unsigned)grid, SC_THREADS, smem, stream>>>(a);
+  }
+  C3P_LAUNCH_CHECK(name);
+  return CONV3P_OK;
+}
+
+int launch_forward_small(const conv3p_geom_t* g, const PlanView& v, const float* input, const float* filter,
+                         int Cin, int Cout, float* output, cudaStream_t stream) {
+  SCArgs a{};
+  a.src = input; a.filter = filter; a.out = output; a.cnt = v.count_table; a.begin = v.pair_begin;
+  a.len = v.pair_len; a.rows = v.pair_row; a.weights = nullptr; a.sorted_xyzi = v.sorted_xyzi;
+  a.total_points = (long long)g->B * g->N; a.capacity = g->pair_capacity; a.N = g->N;
+  a.Cin = Cin; a.Cout = Cout; a.Csrc = Cin; a.Nout = Cout; a.transposed = 0;
+  return launch_small_gc(a, "k_small_forward", stream);
+}
+
+int launch_backward_input_small(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
+                                const float* filter, int Cin, int Cout, float* grad_input,
+                                cudaStream_t stream) {
+  SCArgs a{};
+  a.src = grad_out; a.filter = filter; a.out = grad_input; a.cnt = v.bwd_count; a.begin = v.pair_begin;
+  a.len = v.pair_len; a.rows = v.bwd_row; a.weights = v.bwd_weight; a.sorted_xyzi = v.sorted_xyzi;
+  a.total_points = (long long)g->B * g->N; a.capacity = g->pair_capacity; a.N = g->N;
+  a.Cin = Cin; a.Cout = Cout; a.Csrc = Cout; a.Nout = Cin; a.transposed = 1;
+  return launch_small_gc(a, "k_small_backward_input", stream);
+}
+
+size_t backward_filter_small_scratch_bytes(int Cin, int Cout) {
+  return align_up(sizeof(float) * (size_t)4 * 256 * C3P_NCELL * Cin * Cout);  // up to 4 CTAs on up to 256 SMs
+}
+
+int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
+                                 const float* input, int Cin, int Cout, float* grad_filter, void* scratch,
+                                 size_t scratch_bytes, cudaStream_t stream) {
+  const int nW = C3P_NCELL * Cin * Cout;
+  const long long pts = (long long)g->B * g->N;
+  if (pts == 0) {
+    C3P_CUDA(cudaMemsetAsync(grad_filter, 0, sizeof(float) * nW, stream));
+    return CONV3P_OK;
+  }
+  if (!scratch || scratch_bytes < backward_filter_small_scratch_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
+  SFArgs a{};
+  a.grad_out = grad_out; a.input = input; a.cnt = v.bwd_count; a.begin = v.pair_begin; a.len = v.pair_len;
+  a.rows = v.bwd_row; a.weights = v.bwd_weight; a.sorted_xyzi = v.sorted_xyzi;
+  a.partial = static_cast<float*>(scratch);
+  a.total_points = pts; a.capacity = g->pair_capacity; a.N = g->N; a.Cin = Cin; a.Cout = Cout;
+  const size_t smem = sizeof(float) * (size_t)SC_WARPS * nW;
+  if (smem > 48 * 1024)
+    C3P_CUDA(cudaFuncSetAttribute(k_small_backward_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = smem > 100 * 1024 ? 1 : 2;
+  int sms = sc_sms();
+  if (sms > 256) sms = 256;
+  long long grid = (long long)sms * per_sm;
+  const long long need = (pts + SC_WARPS - 1) / SC_WARPS;
+  if (grid > need) grid = need;
+  {
+    LaunchTimer timer_("k_small_backward_filter", stream);
+    k_small_backward_filter<<<(unsigned)grid, SC_THREADS, smem, stream>>>(a);
+  }
+  C3P_LAUNCH_CHECK("k_small_backward_filter");
+  {
+    LaunchTimer timer_("k_reduce_partials", stream);
+    k_small_reduce<<<(nW + 255) / 256, 256, 0, stream>>>(a.partial, (int)grid, nW, grad_filter);
+  }
+  C3P_LAUNCH_CHECK("k_reduce_partials");
+  return CONV3P_OK;
+}
+
+}  // namespace c3p

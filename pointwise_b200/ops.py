@@ -333,8 +333,9 @@ def conv3p_grad(grad_from_next, points, input, filter, stride, voxel_size,
 
 def set_engine(engine: str = "auto") -> str:
     """Selects the contraction engine: "auto" (tensor cores where the shape allows, else SIMT),
-    "simt" (fp32 CUDA cores only) or "tc".  Returns the previous setting."""
-    names = ["auto", "simt", "tc"]
+    "simt" (fp32 CUDA cores only), "tc", or "tile" (the generic fp32 tile kernels only).  Returns the previous
+    setting."""
+    names = ["auto", "simt", "tc", "tile"]
     prev = _lib.lib().conv3p_set_engine(names.index(engine))
     return names[prev]
 

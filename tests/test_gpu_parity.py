@@ -424,3 +424,28 @@ def test_ragged_cloud_sizes_through_tiles(port):
         out = conv3p_forward(plan, dev(pr["input"]), dev(pr["filter"])).cpu().numpy()
         o32, o64, oabs = port.forward(pr["points"], pr["input"], pr["filter"], 1, V, with64=True)
         assert_close_scaled(out, o64, oabs, RTOL, ATOL, f"forward N={N}")
+
+
+@pytest.mark.parametrize("Cin,Cout,stride", [(9, 9, 1), (3, 9, 1), (36, 13, 1), (13, 36, 2), (16, 16, 1), (1, 1, 3)])
+def test_small_channel_engine_and_tile_engine_match_oracle(port, Cin, Cout, stride):
+    """The reference models' layer shapes: the warp-per-point engine ("simt"/auto) and the generic tile
+    engine ("tile") both meet the tolerance, forward and backward."""
+    from pointwise_b200 import NeighborPlan, conv3p_backward, conv3p_forward, set_engine
+    B, N = 3, 700
+    pr = make_problem(B, N, Cin, Cout, "room", seed=17, quantise=0.05 if Cin == 9 else None)
+    plan = NeighborPlan(dev(pr["points"]), stride, V)
+    o32, o64, oabs = port.forward(pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
+    r = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
+    res = {}
+    for eng in ("simt", "tile"):
+        prev = set_engine(eng)
+        try:
+            y = conv3p_forward(plan, dev(pr["input"]), dev(pr["filter"])).cpu().numpy()
+            gi, gf = conv3p_backward(plan, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]))
+        finally:
+            set_engine(prev)
+        assert_close_scaled(y, o64, oabs, RTOL, ATOL, f"forward[{eng}]")
+        assert_close_scaled(gi.cpu().numpy(), r[2], r[3], RTOL, ATOL, f"grad_input[{eng}]")
+        assert_close_scaled(gf.cpu().numpy(), r[4], r[5], RTOL, ATOL, f"grad_filter[{eng}]")
+        res[eng] = y
+    assert res["simt"].shape == res["tile"].shape
