@@ -1,0 +1,67 @@
+"""Turns the round's raw artefacts in gpurun_out/ into the tables committed under profiles/.
+usage: python tools/profile_tables.py  (after the gpurun collection call in profiles/r1_summary.md)"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+NAMES = {"k_gather_mma_tc<2, 0>": "k_forward_tc", "k_gather_mma_tc<2, 1>": "k_backward_input_tc",
+         "k_gather_mma_tc<1, 0>": "k_forward_tc", "k_gather_mma_tc<1, 1>": "k_backward_input_tc"}
+
+
+def ncu_raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    return rows[0], rows[1], rows[2:]
+
+
+def main():
+    hdr, units, rows = ncu_raw(os.path.join(G, "prof_r1_final.ncu-rep"))
+    g = lambda r, k: r[hdr.index(k)]
+    conv = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
+    traffic, lines = {}, []
+    lines.append("| kernel | time ms | DRAM read MB | DRAM write MB | DRAM % | L2 hit % | tensor pipe % | issue active % "
+                 "| warps active % | regs |")
+    lines.append("|---|---|---|---|---|---|---|---|---|---|")
+    for r in rows:
+        kn = g(r, "Kernel Name")
+        key = kn.split("(")[0].replace("void ", "")
+        for a, b in NAMES.items():
+            if a in kn:
+                key = b
+        rd = float(g(r, "dram__bytes_read.sum").replace(",", "")) * conv[units[hdr.index("dram__bytes_read.sum")]]
+        wr = float(g(r, "dram__bytes_write.sum").replace(",", "")) * conv[units[hdr.index("dram__bytes_write.sum")]]
+        traffic[key] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
+                        "time_ms": float(g(r, "gpu__time_duration.sum"))}
+        lines.append(f"| `{key}` | {float(g(r, 'gpu__time_duration.sum')):.3f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | "
+                     f"{float(g(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | "
+                     f"{float(g(r, 'lts__t_sector_hit_rate.pct')):.1f} | "
+                     f"{float(g(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')):.1f} | "
+                     f"{float(g(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active')):.1f} | "
+                     f"{float(g(r, 'sm__warps_active.avg.pct_of_peak_sustained_active')):.1f} | "
+                     f"{g(r, 'launch__registers_per_thread')} |")
+    json.dump({"headline": traffic}, open(os.path.join(P, "kernel_traffic.json"), "w"), indent=1)
+    print("\n".join(lines))
+    for src, dst in [("bench_r1.json", "r1_bench_headline.json"), ("bench_r1_reference.json", "r1_bench_reference_arm.json"),
+                     ("launches_r1.csv", "r1_launches_headline.csv"), ("bench_r1_s3dis_l1.json", "r1_bench_s3dis_l1.json"),
+                     ("bench_r1_s3dis_l5.json", "r1_bench_s3dis_l5.json"), ("bench_r1_modelnet_l2.json", "r1_bench_modelnet_l2.json")]:
+        if os.path.exists(os.path.join(G, src)):
+            open(os.path.join(P, dst), "w").write(open(os.path.join(G, src)).read())
+    d = json.load(open(os.path.join(G, "bench_r1.json")))
+    print("\nheadline:", d["value"], "points/s", d["ms_per_step"], "ms/step; e2e", d["e2e"]["value"], "; cpu", d["cpu_baseline"]["value"])
+    print("roofline:", {k: d["roofline"][k] for k in ("kernel", "achieved", "frac")})
+    for k, v in d["kernels"].items():
+        print("  ", k, v)
+    for w in ("s3dis_l1", "s3dis_l5", "modelnet_l2"):
+        f = os.path.join(G, f"bench_r1_{w}.json")
+        if os.path.exists(f):
+            x = json.load(open(f))
+            print(w, x["value"], x["ms_per_step"], "cpu", x.get("cpu_baseline", {}).get("value"))
+
+
+if __name__ == "__main__":
+    main()
