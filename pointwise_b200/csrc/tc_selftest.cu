@@ -31,7 +31,10 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t idesc = make_idesc_tf32(128, N);
+  const bool probe_b32 = (split & 2) != 0;   // hardware probe: K-major operands stored with the 32B-base swizzle
+  const bool probe_m64 = (split & 4) != 0;   // hardware probe: M = 64 (rows 64..127 of A are ignored)
+  const uint32_t idesc = make_idesc_tf32(probe_m64 ? 64 : 128, N);
+  split &= 1;
 
   uint32_t phase = 0;
   for (int kp = 0; kp < K / PANEL_K; ++kp) {
@@ -42,8 +45,9 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
       float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
       float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       if (!split) h = v;
-      *reinterpret_cast<float4*>(a_hi + panel_chunk_offset(r, c)) = h;
-      *reinterpret_cast<float4*>(a_lo + panel_chunk_offset(r, c)) = l;
+      const uint32_t o = probe_b32 ? panel_chunk_offset_mn(r, c) : panel_chunk_offset(r, c);
+      *reinterpret_cast<float4*>(a_hi + o) = h;
+      *reinterpret_cast<float4*>(a_lo + o) = l;
     }
     for (int e = tid; e < N * 8; e += 128) {
       const int r = e >> 3, c = e & 7;
@@ -51,15 +55,18 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
       float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
       float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       if (!split) h = v;
-      *reinterpret_cast<float4*>(b_hi + panel_chunk_offset(r, c)) = h;
-      *reinterpret_cast<float4*>(b_lo + panel_chunk_offset(r, c)) = l;
+      const uint32_t o = probe_b32 ? panel_chunk_offset_mn(r, c) : panel_chunk_offset(r, c);
+      *reinterpret_cast<float4*>(b_hi + o) = h;
+      *reinterpret_cast<float4*>(b_lo + o) = l;
     }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after_sync();
-      const uint64_t dah = make_smem_desc(smem_u32(a_hi)), dal = make_smem_desc(smem_u32(a_lo));
-      const uint64_t dbh = make_smem_desc(smem_u32(b_hi)), dbl = make_smem_desc(smem_u32(b_lo));
+      // probe: same K-major descriptor, layout type SWIZZLE_128B_BASE32B (1) instead of SWIZZLE_128B (2)
+      const uint64_t lt = probe_b32 ? ((uint64_t)1 << 61) ^ ((uint64_t)2 << 61) : 0;
+      const uint64_t dah = make_smem_desc(smem_u32(a_hi)) ^ lt, dal = make_smem_desc(smem_u32(a_lo)) ^ lt;
+      const uint64_t dbh = make_smem_desc(smem_u32(b_hi)) ^ lt, dbl = make_smem_desc(smem_u32(b_lo)) ^ lt;
 #pragma unroll
       for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
         const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
