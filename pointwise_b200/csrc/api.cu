@@ -257,7 +257,7 @@ int conv3p_plan_stats(const conv3p_geom_t* geom, const void* plan, conv3p_plan_s
 
 size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
   if (check_geom(geom) || check_channels(Cin, Cout)) return 0;
-  // [weight panel images | split-K partials of grad_filter]
+  // [weight panel images | work-item lists of the tensor-core gather kernels | split-K partials of grad_filter]
   size_t filt = backward_filter_scratch_bytes(geom, Cin, Cout);
   if (small_backward_filter_supported(Cin, Cout)) {
     const size_t t = backward_filter_small_scratch_bytes(Cin, Cout);
@@ -267,7 +267,7 @@ size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
     const size_t t = backward_filter_tc_scratch_bytes(geom, Cin, Cout);
     if (t > filt) filt = t;
   }
-  return weight_panel_bytes(Cin, Cout) + filt + 256;
+  return weight_panel_bytes(Cin, Cout) + tc_items_bytes(geom, Cin, Cout) + filt + 256;
 }
 
 int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
@@ -314,7 +314,7 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
   }
   if (grad_filter) {
     if (!input && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
-    const size_t wpb = weight_panel_bytes(Cin, Cout);
+    const size_t wpb = weight_panel_bytes(Cin, Cout) + tc_items_bytes(geom, Cin, Cout);
     if (!scratch || scratch_bytes < wpb) return CONV3P_ERR_BUFFER_TOO_SMALL;
     if (engine() != 1 && backward_filter_tc_supported(geom->N, geom->pair_capacity, Cin, Cout))
       st = launch_backward_filter_tc(geom, v, grad_output, input, Cin, Cout, grad_filter,

@@ -76,6 +76,15 @@ int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* in
                       int Cin, int Cout, float* output, void* scratch, size_t scratch_bytes,
                       cudaStream_t stream);
 
+// second-generation gather + MMA kernel (gather_mma2.cu); engine bit 128 selects the first generation instead
+bool gather_mma2_supported(int N, long long capacity, int Csrc, int Nout);
+size_t gather_mma2_scratch_bytes(const conv3p_geom_t* g);  // work-item lists of one launch
+int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* src, const void* wp, int Csrc,
+                       int Nout, float* out, bool weighted, void* scratch, size_t scratch_bytes, const char* name,
+                       cudaStream_t stream);
+// scratch layout of one forward / backward call: [weight panel images | work-item lists | grad_filter partials]
+size_t tc_items_bytes(const conv3p_geom_t* g, int Cin, int Cout);
+
 bool backward_filter_tc_supported(int N, long long capacity, int Cin, int Cout);
 size_t backward_filter_tc_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout);
 int launch_backward_filter_tc(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,

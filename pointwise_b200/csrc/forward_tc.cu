@@ -34,8 +34,6 @@ constexpr int FT_MAX_NKC = 4;
 // One kernel serves the forward pass (src = input, lists = forward lists, per-cell mean) and the input
 // gradient (src = grad_out, lists = backward lists with per-entry weights 1/count(ii,f'), panels = W
 // itself): out[p, n] = sum_f sum_k A_f[p, k] * Wpanel_f[n, k].
-// phase timers of the producer loop (cycles, warp 0 of every CTA); filled only when engine debug bit 32 is set
-__device__ unsigned long long g_phase_cycles[8];
 
 struct FTArgs {
   const float* src;         // gathered rows [B*N, Csrc]
@@ -199,9 +197,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_gather_mma_tc(const FTArgs a)
     bool have = advance(gf, gkb, gt, gact);
     Slot d0;
     if (have) d0 = fetch(gf, gt, g, 0);
-    unsigned long long ph[7] = {0, 0, 0, 0, 0, 0, 0};
-    long long tc0 = clock64();
-#define C3P_PHASE(i) do { if (a.debug & 32) { long long _t = clock64(); ph[i] += (unsigned long long)(_t - tc0); tc0 = _t; } } while (0)
+#define C3P_PHASE(i) do { } while (0)  /* phase timers moved to gather_mma2.cu */
     while (have) {
       const int col = gkb * NKC * PANEL_K;
       Slot d1;
@@ -244,8 +240,6 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_gather_mma_tc(const FTArgs a)
       d0 = dn;
       C3P_PHASE(6);
     }
-    if ((a.debug & 32) && warp == 0 && lane == 0)
-      for (int i = 0; i < 7; ++i) atomicAdd(&g_phase_cycles[i], ph[i]);
     // =========================== epilogue: TMEM -> registers -> global ==============================
     mbar_wait(&acc_full, 0);
     tc_fence_after_sync();
@@ -400,6 +394,13 @@ bool backward_input_tc_supported(int N, long long capacity, int Cin, int Cout) {
 
 size_t weight_panel_bytes(int Cin, int Cout) { return align_up((size_t)2 * C3P_NCELL * Cin * Cout * 4); }
 
+size_t tc_items_bytes(const conv3p_geom_t* g, int Cin, int Cout) {
+  if (gather_mma2_supported(g->N, g->pair_capacity, Cin, Cout) ||
+      gather_mma2_supported(g->N, g->pair_capacity, Cout, Cin))
+    return gather_mma2_scratch_bytes(g);
+  return 0;
+}
+
 int launch_prep_weight_panels(const float* filter, void* wp, int Cin, int Cout, int transposed_out,
                               cudaStream_t stream) {
   const long long total = (long long)C3P_NCELL * Cin * Cout;
@@ -417,7 +418,7 @@ int launch_prep_weight_panels(const float* filter, void* wp, int Cin, int Cout, 
 static int launch_gather_mma(FTArgs& a, const FTConfig& c, bool weighted, const char* name,
                              cudaStream_t stream) {
   a.nkb = c.nkb; a.T = c.T; a.NWS = c.NWS;
-  a.debug = engine() >= 64 ? (engine() & ~64) : 0;
+  a.debug = engine() >= 64 ? (engine() & ~(64 | 128)) : 0;
   const long long tiles = (a.total_points + (long long)a.T * 128 - 1) / ((long long)a.T * 128);
   if (tiles == 0) return CONV3P_OK;
   auto launch = [&](auto kern) -> int {
@@ -441,6 +442,11 @@ int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* in
   if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
   int st = launch_prep_weight_panels(filter, scratch, Cin, Cout, 0, stream);
   if (st) return st;
+  if (!(engine() & 128) && gather_mma2_supported(g->N, g->pair_capacity, Cin, Cout)) {
+    const size_t wpb = weight_panel_bytes(Cin, Cout);
+    return launch_gather_mma2(g, v, input, scratch, Cin, Cout, output, false, static_cast<char*>(scratch) + wpb,
+                              scratch_bytes - wpb, "k_forward_tc", stream);
+  }
   FTArgs a{};
   a.src = input; a.wp = static_cast<const unsigned char*>(scratch); a.out = output;
   a.cnt = v.count_table; a.begin = v.pair_begin; a.len = v.pair_len; a.rows = v.pair_row;
@@ -458,6 +464,11 @@ int launch_backward_input_tc(const conv3p_geom_t* g, const PlanView& v, const fl
   if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
   int st = launch_prep_weight_panels(filter, scratch, Cin, Cout, 1, stream);
   if (st) return st;
+  if (!(engine() & 128) && gather_mma2_supported(g->N, g->pair_capacity, Cout, Cin)) {
+    const size_t wpb = weight_panel_bytes(Cin, Cout);
+    return launch_gather_mma2(g, v, grad_out, scratch, Cout, Cin, grad_input, true,
+                              static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, "k_backward_input_tc", stream);
+  }
   FTArgs a{};
   a.src = grad_out; a.wp = static_cast<const unsigned char*>(scratch); a.out = grad_input;
   a.cnt = v.bwd_count; a.begin = v.pair_begin; a.len = v.pair_len; a.rows = v.bwd_row;
@@ -468,11 +479,3 @@ int launch_backward_input_tc(const conv3p_geom_t* g, const PlanView& v, const fl
 }
 
 }  // namespace c3p
-
-// profiling helper (tools/engine_timing.py): read and clear the producer phase timers
-extern "C" int conv3p_debug_phase_cycles(unsigned long long* host8) {
-  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (cudaMemcpyFromSymbol(host8, c3p::g_phase_cycles, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;
-  if (cudaMemcpyToSymbol(c3p::g_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;
-  return CONV3P_OK;
-}

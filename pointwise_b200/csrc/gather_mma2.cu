@@ -1,0 +1,614 @@
+// gather_mma2.cu -- second-generation fused gather + 3xTF32 tcgen05 kernel (forward and grad_input).
+//
+// Same contraction as forward_tc.cu (see there for the maths and the operand layout):
+//   out[p, n] = sum_f sum_k A_f[p, k] * Wpanel_f[n, k],   A_f = per-cell mean (forward, tf_conv3p_atrous.cpp:
+//   480-494) or weighted sum over the backward lists (grad_input, :682-692),
+// but the CUDA-core side of the fusion -- which bounded the first version (profiles/r1_summary.md: 4548 producer
+// cycles per (cell, sub-tile) group against 1572 cycles of MMA work) -- is reorganised:
+//
+//  * A PRE-PASS (k_group_items, one warp per 128-point sub-tile) turns the count table into, for every (sub-tile,
+//    cell) group, a list of 128 work items (list position, row, members), 1 KB per group, in scratch memory; the
+//    main kernel streams the lists of its groups into a small shared-memory ring with bulk async copies.
+//    Items are compacted by population class (> 8 members, 5..8, 1..4, empty), so the producer quarter-warps
+//    of one warp see similar list lengths, the second repetition of a group is usually all-empty (58 % of the
+//    (row, cell) slots are empty on the S3DIS-like bench cloud) and is then a plain zero fill, and the
+//    producers no longer keep per-point prefix tables (28 KB) in shared memory.  (An in-kernel scheduler warp
+//    doing the same ranking was measured first: it needed ~4500 cycles per group and paced the whole CTA.)
+//  * The gather itself selects on the ADDRESS and the WEIGHT, never on the loaded value: absent members
+//    re-read a valid row with weight 0 and every accumulation is a packed FFMA2, which removes the
+//    zero-select instructions (one third of the old inner loop).
+//  * The freed shared memory deepens the operand ring from 3 to 4-5 stages (two full groups in flight), and
+//    weight panels are streamed in hi / lo units so one extra unit is enough to prefetch the next cell.
+//
+// Warp roles: warps [0, NPW) producers (also the epilogue), NPW = MMA issuer, NPW+1 = weight loader + TMEM
+// allocator, NPW+2 = item-list loader.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace c3p {
+
+using namespace tc;
+
+constexpr int G2_NPW = 16;
+constexpr int G2_WARPS = G2_NPW + 3;
+constexpr int G2_THREADS = G2_WARPS * 32;
+constexpr int G2_NIS = 4;                              // item-list slots (groups the scheduler may run ahead)
+constexpr int G2_A_STAGE = 2 * 128 * PANEL_ROW_BYTES;  // hi + lo panels of 128 rows x 32 channels
+constexpr int G2_MAX_NAS = 6, G2_MAX_NWU = 8, G2_MAXT = 4;
+constexpr int G2_END = -1;
+
+struct G2Args {
+  const float* src;         // gathered rows [B*N, Csrc]
+  const unsigned char* wp;  // weight panel images [27][Csrc/32][hi,lo][Nout][128 B] (k_prep_weight_panels)
+  float* out;               // [B*N, Nout]
+  const int* rows;          // list entries: row ids
+  const float* weights;     // per-entry weights (WEIGHTED) or nullptr (per-cell mean)
+  const uint2* g_items;     // [subtiles][27][128] work items (k_group_items)
+  const int* g_nnz;         // [subtiles][27] non-empty rows of the group
+  const int* g_rowid;       // [subtiles*128] output row of every sorted position (-1 pad, -2-row poisoned)
+  long long total_points, subtiles;
+  int N, Csrc, Nout, nkb, T, NAS, NWU;
+  int debug;  // bit 32: accumulate the phase timers below
+};
+
+// cycles summed over CTAs (warp 0, lane 0): prologue | producer loop | wait for the last MMA | epilogue |
+// in the loop: item fetch | first gather | wait for a free ring stage | stores + second repetition + arrive
+__device__ unsigned long long g2_phase_cycles[8];
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// acc += w * v on both halves of a float4 (two FFMA2)
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+  const float2 ww = make_float2(w, w);
+  const float2 lo = __ffma2_rn(ww, make_float2(v.x, v.y), make_float2(acc.x, acc.y));
+  const float2 hi = __ffma2_rn(ww, make_float2(v.z, v.w), make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+struct G2Item {
+  uint32_t pos;   // position of the cell's first entry in the list arrays
+  int p;          // row of the sub-tile (0..127)
+  int n;          // members (0: store zeros)
+  float inv;      // 1 / n (unweighted lists; MUFU reciprocal, within 1 ulp)
+  int ids;        // lane l8: row id of entry l8 of the list (prefetched)
+  float w;        // lane l8: its weight (WEIGHTED)
+};
+
+template <bool WEIGHTED>
+__device__ __forceinline__ void g2_prefetch(G2Item& it, const int* __restrict__ rows,
+                                            const float* __restrict__ weights, int m0, int l8,
+                                            unsigned max_row) {
+  // select on the ADDRESS: nothing consumes the loaded values until the item is gathered
+  const uint32_t at = it.n > 0 ? it.pos + (uint32_t)min(m0 + l8, it.n - 1) : 0u;
+  it.ids = (int)min((unsigned)__ldg(rows + at), max_row);
+  if (WEIGHTED) it.w = __ldg(weights + at);
+}
+
+// acc[kc] = sum_m w_m * src[list[m], col + kc*32 + l8*4 .. +4].  Called by all 32 lanes; n is uniform inside a
+// quarter-warp and the trip count is made warp-uniform (the id broadcast is a shuffle).
+template <int NKC, bool WEIGHTED>
+__device__ __forceinline__ void g2_gather(float4 (&acc)[NKC], G2Item& it, int nmax,
+                                          const float* __restrict__ src, int Csrc, int col,
+                                          const int* __restrict__ rows, const float* __restrict__ weights,
+                                          int l8, unsigned max_row) {
+#pragma unroll
+  for (int kc = 0; kc < NKC; ++kc) acc[kc] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* base = src + col + l8 * 4;
+  for (int m0 = 0; m0 < nmax; m0 += 4) {
+    if (m0 && !(m0 & 7)) g2_prefetch<WEIGHTED>(it, rows, weights, m0, l8, max_row);
+    float4 v[4][NKC];
+    float wv[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int id = __shfl_sync(C3P_FULL_MASK, it.ids, (m0 + m) & 7, 8);
+      float w = it.inv;
+      if (WEIGHTED) w = __shfl_sync(C3P_FULL_MASK, it.w, (m0 + m) & 7, 8);
+      wv[m] = (m0 + m < it.n) ? w : 0.f;
+      const float* p = base + (size_t)id * Csrc;
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) v[m][kc] = ldg4(p + kc * PANEL_K);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) fma4(acc[kc], wv[m], v[m][kc]);
+  }
+}
+
+__device__ __forceinline__ void g2_store_split(unsigned char* dst, const float4& v) {
+  const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  const float2 l0 = __fadd2_rn(make_float2(v.x, v.y), make_float2(-h.x, -h.y));
+  const float2 l1 = __fadd2_rn(make_float2(v.z, v.w), make_float2(-h.z, -h.w));
+  *reinterpret_cast<float4*>(dst) = h;
+  *reinterpret_cast<float4*>(dst + 128 * PANEL_ROW_BYTES) = make_float4(l0.x, l0.y, l1.x, l1.y);
+}
+
+// ---- pre-pass: compacted work-item lists per (sub-tile, cell) group ---------------------------------------------
+// One warp per sub-tile of 128 voxel-sorted points; lane l owns rows l, l+32, l+64, l+96 and carries their list
+// positions across the 27 cells.  Within a group the rows are ranked by population class (0: more than 8 members,
+// 1: 5..8, 2: 1..4, 3: empty) with ballots, so item index = class base + rank inside the class.
+constexpr int GI_WARPS = 8;
+
+__global__ void __launch_bounds__(GI_WARPS * 32)
+k_group_items(const int* __restrict__ cnt, const long long* __restrict__ begin, const int* __restrict__ len,
+              const float4* __restrict__ sorted_xyzi, long long total_points, long long capacity, int N,
+              long long subtiles, uint2* __restrict__ g_items, int* __restrict__ g_nnz, int* __restrict__ g_rowid) {
+  const long long sub = (long long)blockIdx.x * GI_WARPS + (threadIdx.x >> 5);
+  if (sub >= subtiles) return;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = lanemask_lt();
+  uint32_t pos[4];
+  const int* crow[4];
+  bool ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long s = sub * 128 + lane + 32 * i;
+    int row = -1;
+    pos[i] = 0;
+    ok[i] = false;
+    crow[i] = cnt;
+    if (s < total_points) {
+      const int b = (int)(s / N);
+      row = b * N + __float_as_int(sorted_xyzi[s].w);
+      const long long bg = begin[row];
+      ok[i] = bg + len[row] <= capacity;
+      pos[i] = (uint32_t)bg;
+      crow[i] = cnt + (size_t)row * C3P_NCELL;
+      if (!ok[i]) row = -2 - row;  // incomplete list: the main kernel poisons this point's output
+    }
+    g_rowid[s] = row;
+  }
+  uint2* out = g_items + sub * C3P_NCELL * 128;
+  constexpr int FB = 9;  // cells per batch of count loads
+  for (int f0 = 0; f0 < C3P_NCELL; f0 += FB) {
+    int c[FB][4];
+#pragma unroll
+    for (int j = 0; j < FB; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[j][i] = ok[i] ? __ldg(crow[i] + f0 + j) : 0;
+#pragma unroll
+    for (int j = 0; j < FB; ++j) {
+      unsigned m[4][4];
+      int cls[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = c[j][i];
+        cls[i] = n > 8 ? 0 : (n > 4 ? 1 : (n > 0 ? 2 : 3));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[k][i] = __ballot_sync(C3P_FULL_MASK, cls[i] == k);
+      }
+      int base[4];
+      int run = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        base[k] = run;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) run += __popc(m[k][i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int idx = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (cls[i] == k) {
+            idx = base[k] + __popc(m[k][i] & lt);
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2)
+              if (i2 < i) idx += __popc(m[k][i2]);
+          }
+        }
+        out[(f0 + j) * 128 + idx] = make_uint2(pos[i], (uint32_t)(lane + 32 * i) | ((uint32_t)c[j][i] << 8));
+        pos[i] += (uint32_t)c[j][i];
+      }
+      if (lane == 0) g_nnz[sub * C3P_NCELL + f0 + j] = base[3];  // rows of classes 0..2
+    }
+  }
+}
+
+
+template <int NKC, bool WEIGHTED>
+__global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int T = a.T, Nout = a.Nout, NAS = a.NAS, NWU = a.NWU;
+  const int PT = T * 128;
+  const uint32_t unit_bytes = (uint32_t)Nout * PANEL_ROW_BYTES;       // hi (or lo) half of a weight panel
+  unsigned char* a_base = smem;                                       // NAS stages
+  unsigned char* w_base = a_base + (size_t)NAS * G2_A_STAGE;          // NWU units
+  uint2* items = reinterpret_cast<uint2*>(w_base + (size_t)NWU * unit_bytes);  // [NIS][128]
+  int* rowid = reinterpret_cast<int*>(items + G2_NIS * 128);          // [PT]
+  __shared__ uint64_t a_full[G2_MAX_NAS], a_empty[G2_MAX_NAS], w_full[G2_MAX_NWU], w_empty[G2_MAX_NWU],
+      it_full[G2_NIS], it_empty[G2_NIS], acc_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ unsigned active[C3P_NCELL];  // bit t: sub-tile t has members in cell f
+  __shared__ int hdr[G2_NIS];             // K batch of the group in the slot, or G2_END
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long s0 = (long long)blockIdx.x * PT;
+  const bool timed = (a.debug & 32) && tid == 0;
+  long long tk = timed ? clock64() : 0;
+  unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define G2_PHASE(i) do { if (timed) { const long long t_ = clock64(); ph[i] += (unsigned long long)(t_ - tk); tk = t_; } } while (0)
+
+  if (tid < C3P_NCELL) active[tid] = 0;
+  if (warp == G2_NPW && lane == 0) {
+    for (int i = 0; i < NAS; ++i) {
+      mbar_init(&a_full[i], G2_NPW);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < NWU; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < G2_NIS; ++i) {
+      mbar_init(&it_full[i], 1);
+      mbar_init(&it_empty[i], G2_NPW);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == G2_NPW + 1) tmem_alloc(&tmem_slot, 512);
+  __syncthreads();
+  // ---- output rows of the tile and which (cell, sub-tile) groups have members at all ---------------------------
+  const long long sub0 = (long long)blockIdx.x * T;
+  for (int p = tid; p < PT; p += G2_THREADS)
+    rowid[p] = (sub0 + (p >> 7) < a.subtiles) ? __ldg(a.g_rowid + s0 + p) : -1;
+  if (tid < C3P_NCELL * T) {
+    const int t = tid / C3P_NCELL, f = tid - t * C3P_NCELL;
+    if (sub0 + t < a.subtiles && __ldg(a.g_nnz + (sub0 + t) * C3P_NCELL + f) > 0) atomicOr(&active[f], 1u << t);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const unsigned max_row = (unsigned)(a.total_points - 1);
+  G2_PHASE(0);
+
+  if (warp < G2_NPW) {
+    // =========================== producers: gather -> mean -> hi/lo -> operand panels ===================
+    // Quarter-warp q serves items (q + 4g) mod 64 and 64 + that of group g; lane l8 owns one 16-byte chunk of
+    // the row segment.  Software-pipelined: the item and the list ids of the next group are fetched before
+    // the rows of the current group are gathered.
+    const int q = warp * 4 + (lane >> 3);
+    const int l8 = lane & 7;
+    auto read_items = [&](int g_, G2Item& i0, G2Item& i1) -> int {
+      const int slot = g_ & (G2_NIS - 1);
+      mbar_wait(&it_full[slot], (uint32_t)((g_ / G2_NIS) & 1));
+      const int h = hdr[slot];
+      const int e = (q + 4 * g_) & 63;
+      const uint2 u0 = items[slot * 128 + e], u1 = items[slot * 128 + 64 + e];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&it_empty[slot]);
+      const bool live = h != G2_END;
+      i0.pos = u0.x; i0.p = (int)(u0.y & 255u); i0.n = live ? (int)(u0.y >> 8) : 0;
+      i1.pos = u1.x; i1.p = (int)(u1.y & 255u); i1.n = live ? (int)(u1.y >> 8) : 0;
+      i0.inv = WEIGHTED ? 0.f : __fdividef(1.f, (float)i0.n);
+      i1.inv = WEIGHTED ? 0.f : __fdividef(1.f, (float)i1.n);
+      i0.w = 0.f; i1.w = 0.f;
+      g2_prefetch<WEIGHTED>(i0, a.rows, a.weights, 0, l8, max_row);
+      g2_prefetch<WEIGHTED>(i1, a.rows, a.weights, 0, l8, max_row);
+      return h;
+    };
+    auto warp_max = [&](int n) -> int {
+      n = max(n, __shfl_xor_sync(C3P_FULL_MASK, n, 8));
+      return max(n, __shfl_xor_sync(C3P_FULL_MASK, n, 16));
+    };
+    int g = 0, aslot = 0;
+    uint32_t awrap = 0;  // times the ring wrapped before stage `aslot`
+    G2Item c0, c1;
+    int hc = read_items(0, c0, c1);
+    long long tl = timed ? clock64() : 0;
+    while (hc != G2_END) {
+      G2Item n0, n1;
+      const int hn = read_items(g + 1, n0, n1);
+      G2_PHASE(4);
+      const int col = hc * NKC * PANEL_K;
+      float4 acc[NKC];
+      g2_gather<NKC, WEIGHTED>(acc, c0, warp_max(c0.n), a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
+      G2_PHASE(5);
+      // the ring stages of this group must have been drained by the tensor core
+      unsigned char* stage[NKC];
+      {
+        int sl = aslot;
+        uint32_t wr = awrap;
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+          if (wr >= 1) mbar_wait(&a_empty[sl], (wr - 1) & 1u);
+          stage[kc] = a_base + (size_t)sl * G2_A_STAGE;
+          if (++sl == NAS) { sl = 0; ++wr; }
+        }
+      }
+      G2_PHASE(6);
+      {
+        const uint32_t o = panel_chunk_offset(c0.p, l8);
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, acc[kc]);
+      }
+      const int nmax1 = warp_max(c1.n);
+      if (nmax1 > 0)
+        g2_gather<NKC, WEIGHTED>(acc, c1, nmax1, a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
+      {
+        const uint32_t o = panel_chunk_offset(c1.p, l8);
+        if (nmax1 > 0) {
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, acc[kc]);
+        } else {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) {
+            *reinterpret_cast<float4*>(stage[kc] + o) = z;
+            *reinterpret_cast<float4*>(stage[kc] + o + 128 * PANEL_ROW_BYTES) = z;
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        int sl = aslot;
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+          mbar_arrive(&a_full[sl]);
+          if (++sl == NAS) sl = 0;
+        }
+      }
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc)
+        if (++aslot == NAS) { aslot = 0; ++awrap; }
+      ++g;
+      c0 = n0; c1 = n1; hc = hn;
+      G2_PHASE(7);
+    }
+    if (timed) { tk = clock64(); ph[1] = (unsigned long long)(tk - tl); }
+    // =========================== epilogue: TMEM -> registers -> global ==============================
+    mbar_wait(&acc_full, 0);
+    tc_fence_after_sync();
+    G2_PHASE(2);
+    for (int task = warp; task < 4 * T; task += G2_NPW) {
+      const int t = task >> 2, sub = task & 3;
+      bool any = false;
+      for (int f = 0; f < C3P_NCELL; ++f) any |= ((active[f] >> t) & 1u) != 0;
+      const int pt = t * 128 + sub * 32 + lane;
+      int row = rowid[pt];
+      const bool poison = row < -1;
+      if (poison) row = -2 - row;
+      for (int c0_ = 0; c0_ < Nout; c0_ += 32) {
+        float v[32];
+        if (any) {
+          tmem_ld_32x32(tmem + ((uint32_t)(sub * 32) << 16) + (uint32_t)(t * Nout + c0_), v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (row >= 0) {
+          float* o = a.out + (size_t)row * Nout + c0_;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c0_ + j < Nout) {
+              float4 w4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (poison) w4 = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
+                                           __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+              *reinterpret_cast<float4*>(o + j) = w4;
+            }
+          }
+        }
+      }
+    }
+    G2_PHASE(3);
+    if (timed)
+      for (int i = 0; i < 8; ++i) atomicAdd(&g2_phase_cycles[i], ph[i]);
+  } else if (warp == G2_NPW) {
+    // =========================== MMA issuer (one thread) ============================================
+    // Per 32-channel panel: 4 K steps of (A_hi W_hi, A_lo W_hi), then 4 K steps of A_hi W_lo, so the lo half of
+    // a weight panel is needed 512 MMA cycles after its hi half and the hi unit is released before the lo unit.
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, Nout);
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(a_base)), w_desc0 = make_smem_desc(smem_u32(w_base));
+      const uint64_t a_lo_off = (uint64_t)((128 * PANEL_ROW_BYTES) >> 4);
+      const uint64_t a_step = (uint64_t)(G2_A_STAGE >> 4), w_step = (uint64_t)(unit_bytes >> 4);
+      unsigned started = 0;
+      int aslot = 0, wslot = 0;
+      uint32_t aphase = 0, wphase = 0;
+      for (int f = 0; f < C3P_NCELL; ++f) {
+        const unsigned act = active[f];
+        if (!act) continue;
+        const int t_first = __ffs(act) - 1, t_last = 31 - __clz(act);
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          int us[2 * NKC];
+          uint32_t up[2 * NKC];
+#pragma unroll
+          for (int i = 0; i < 2 * NKC; ++i) {
+            us[i] = wslot; up[i] = wphase;
+            if (++wslot == NWU) { wslot = 0; wphase ^= 1u; }
+          }
+          for (int t = 0; t < T; ++t) {
+            if (!((act >> t) & 1u)) continue;
+            const uint32_t d = tmem + (uint32_t)(t * Nout);
+            uint32_t acc_flag = (started >> t) & 1u;
+            started |= 1u << t;
+#pragma unroll
+            for (int kc = 0; kc < NKC; ++kc) {
+              if (t == t_first) mbar_wait(&w_full[us[2 * kc]], up[2 * kc]);
+              mbar_wait(&a_full[aslot], aphase);
+              tc_fence_after_sync();
+              const uint64_t dah = a_desc0 + (uint64_t)aslot * a_step, dal = dah + a_lo_off;
+              const uint64_t dwh = w_desc0 + (uint64_t)us[2 * kc] * w_step;
+              const uint64_t dwl = w_desc0 + (uint64_t)us[2 * kc + 1] * w_step;
+#pragma unroll
+              for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                mma_tf32(d, dah + adv, dwh + adv, idesc, acc_flag);
+                mma_tf32(d, dal + adv, dwh + adv, idesc, 1u);
+                acc_flag = 1u;
+              }
+              if (t == t_last) mma_commit(&w_empty[us[2 * kc]]);
+              if (t == t_first) {
+                mbar_wait(&w_full[us[2 * kc + 1]], up[2 * kc + 1]);
+                tc_fence_after_sync();
+              }
+#pragma unroll
+              for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                mma_tf32(d, dah + adv, dwl + adv, idesc, 1u);
+              }
+              mma_commit(&a_empty[aslot]);
+              if (t == t_last) mma_commit(&w_empty[us[2 * kc + 1]]);
+              if (++aslot == NAS) { aslot = 0; aphase ^= 1u; }
+            }
+          }
+        }
+      }
+      mma_commit(&acc_full);
+    }
+  } else if (warp == G2_NPW + 1) {
+    // =========================== weight loader (one thread) =========================================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t wrap = 0;
+      const int units_per_cell = a.nkb * NKC * 2;
+      for (int f = 0; f < C3P_NCELL; ++f) {
+        if (!active[f]) continue;
+        for (int u = 0; u < units_per_cell; ++u) {
+          if (wrap >= 1) mbar_wait(&w_empty[slot], (wrap - 1) & 1u);
+          mbar_arrive_expect_tx(&w_full[slot], unit_bytes);
+          bulk_copy_g2s(w_base + (size_t)slot * unit_bytes,
+                        a.wp + ((size_t)f * units_per_cell + u) * unit_bytes, unit_bytes, &w_full[slot]);
+          if (++slot == NWU) { slot = 0; ++wrap; }
+        }
+      }
+    }
+  } else {
+    // =========================== item-list loader (one thread) ======================================
+    if (lane == 0) {
+      int g = 0;
+      for (int f = 0; f < C3P_NCELL; ++f) {
+        const unsigned act = active[f];
+        if (!act) continue;
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          for (int t = 0; t < T; ++t) {
+            if (!((act >> t) & 1u)) continue;
+            const int slot = g & (G2_NIS - 1), use = g / G2_NIS;
+            if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
+            hdr[slot] = kb;
+            mbar_arrive_expect_tx(&it_full[slot], 128 * sizeof(uint2));
+            bulk_copy_g2s(items + slot * 128, a.g_items + ((sub0 + t) * C3P_NCELL + f) * 128, 128 * sizeof(uint2),
+                          &it_full[slot]);
+            ++g;
+          }
+        }
+      }
+      const int slot = g & (G2_NIS - 1), use = g / G2_NIS;
+      if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
+      hdr[slot] = G2_END;
+      mbar_arrive(&it_full[slot]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == G2_NPW + 1) tmem_dealloc(tmem, 512);
+}
+
+struct G2Config {
+  int NKC, nkb, T, NAS, NWU;
+  size_t smem;
+};
+
+// Csrc = contraction width per cell (Cin forward, Cout backward), Nout = output width.
+static bool g2_config(int N, long long capacity, int Csrc, int Nout, G2Config* c, long long points = 0) {
+  if (N > 65535) return false;                // members per cell are packed in 24 bits, rows in 8
+  if (capacity >= (1LL << 32)) return false;  // list positions are 32-bit
+  if (Csrc % 32 || Nout % 16 || Csrc < 32 || Nout < 16 || Nout > 256) return false;
+  c->NKC = (Csrc % 64 == 0) ? 2 : 1;
+  c->nkb = Csrc / (32 * c->NKC);
+  c->T = 512 / Nout >= 4 ? 4 : (512 / Nout);
+  // Wave quantisation (one CTA per SM): a smaller T can need fewer sub-tile rounds in total.
+  if (points > 0 && c->T == 4) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    (void)cudaGetLastError();
+    auto rounds = [&](int T) {
+      const long long tiles = (points + (long long)T * 128 - 1) / ((long long)T * 128);
+      return ((tiles + sms - 1) / sms) * T;
+    };
+    if (rounds(3) < rounds(4)) c->T = 3;
+  }
+  const size_t budget = 227 * 1024 - 2048;  // static shared memory (barriers, masks) + alignment slack
+  const size_t unit = (size_t)Nout * PANEL_ROW_BYTES;
+  const size_t tables = (size_t)c->T * 128 * 4 + (size_t)G2_NIS * 128 * 8;
+  c->NWU = 2 * c->NKC;
+  if (tables + c->NWU * unit > budget) return false;
+  size_t room = budget - tables - c->NWU * unit;
+  c->NAS = (int)(room / G2_A_STAGE);
+  if (c->NAS > G2_MAX_NAS) c->NAS = G2_MAX_NAS;
+  if (c->NAS < c->NKC + 1) return false;
+  room -= (size_t)c->NAS * G2_A_STAGE;
+  int extra = (int)(room / unit);
+  if (extra > 2) extra = 2;
+  c->NWU += extra;
+  c->smem = (size_t)c->NAS * G2_A_STAGE + (size_t)c->NWU * unit + tables;
+  return true;
+}
+
+bool gather_mma2_supported(int N, long long capacity, int Csrc, int Nout) {
+  G2Config c;
+  return g2_config(N, capacity, Csrc, Nout, &c);
+}
+
+// scratch of one launch: [items | nnz | rowid]
+static size_t g2_items_bytes(long long subtiles) { return align_up((size_t)subtiles * C3P_NCELL * 128 * sizeof(uint2)); }
+static size_t g2_nnz_bytes(long long subtiles) { return align_up((size_t)subtiles * C3P_NCELL * sizeof(int)); }
+size_t gather_mma2_scratch_bytes(const conv3p_geom_t* g) {
+  const long long subtiles = ((long long)g->B * g->N + 127) / 128;
+  return g2_items_bytes(subtiles) + g2_nnz_bytes(subtiles) + align_up((size_t)subtiles * 128 * sizeof(int));
+}
+
+int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* src, const void* wp, int Csrc,
+                       int Nout, float* out, bool weighted, void* scratch, size_t scratch_bytes, const char* name,
+                       cudaStream_t stream) {
+  G2Config c;
+  const long long pts = (long long)g->B * g->N;
+  if (!g2_config(g->N, g->pair_capacity, Csrc, Nout, &c, pts)) return CONV3P_ERR_UNSUPPORTED;
+  if (pts == 0) return CONV3P_OK;
+  if (!scratch || scratch_bytes < gather_mma2_scratch_bytes(g)) return CONV3P_ERR_BUFFER_TOO_SMALL;
+  const long long subtiles = (pts + 127) / 128;
+  char* sp = static_cast<char*>(scratch);
+  uint2* g_items = reinterpret_cast<uint2*>(sp);
+  int* g_nnz = reinterpret_cast<int*>(sp + g2_items_bytes(subtiles));
+  int* g_rowid = reinterpret_cast<int*>(sp + g2_items_bytes(subtiles) + g2_nnz_bytes(subtiles));
+  {
+    LaunchTimer timer_("k_group_items", stream);
+    k_group_items<<<(unsigned)((subtiles + GI_WARPS - 1) / GI_WARPS), GI_WARPS * 32, 0, stream>>>(
+        weighted ? v.bwd_count : v.count_table, v.pair_begin, v.pair_len, v.sorted_xyzi, pts, g->pair_capacity,
+        g->N, subtiles, g_items, g_nnz, g_rowid);
+  }
+  C3P_LAUNCH_CHECK("k_group_items");
+  G2Args a{};
+  a.src = src; a.wp = static_cast<const unsigned char*>(wp); a.out = out;
+  a.rows = weighted ? v.bwd_row : v.pair_row;
+  a.weights = weighted ? v.bwd_weight : nullptr;
+  a.g_items = g_items; a.g_nnz = g_nnz; a.g_rowid = g_rowid;
+  a.total_points = pts; a.subtiles = subtiles;
+  a.N = g->N; a.Csrc = Csrc; a.Nout = Nout;
+  a.nkb = c.nkb; a.T = c.T; a.NAS = c.NAS; a.NWU = c.NWU;
+  a.debug = engine() >= 64 ? (engine() & ~(64 | 128)) : 0;
+  const long long tiles = (subtiles + c.T - 1) / c.T;
+  auto launch = [&](auto kern) -> int {
+    C3P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    {
+      LaunchTimer timer_(name, stream);
+      kern<<<(unsigned)tiles, G2_THREADS, c.smem, stream>>>(a);
+    }
+    C3P_LAUNCH_CHECK(name);
+    return CONV3P_OK;
+  };
+  if (c.NKC == 1) return weighted ? launch(k_gather_mma2<1, true>) : launch(k_gather_mma2<1, false>);
+  return weighted ? launch(k_gather_mma2<2, true>) : launch(k_gather_mma2<2, false>);
+}
+
+}  // namespace c3p
+
+// profiling helper (tools/engine_timing.py): read and clear the phase timers of k_gather_mma2
+extern "C" int conv3p_debug_phase_cycles(unsigned long long* host8) {
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(host8, c3p::g2_phase_cycles, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;
+  if (cudaMemcpyToSymbol(c3p::g2_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;
+  return CONV3P_OK;
+}

@@ -23,12 +23,28 @@ for eng, name in [(0, "auto"), (1, "simt")]:
 L.conv3p_set_engine(0)
 
 import ctypes as C
-L.conv3p_set_engine(64 + 32)
 buf = (C.c_ulonglong * 8)()
-L.conv3p_debug_phase_cycles(buf)
-conv3p_forward(plan, pr["input"], pr["filter"]); torch.cuda.synchronize()
-L.conv3p_debug_phase_cycles(buf)
-groups = 683 * 81
-print("forward producer, warp 0, cycles per group:", [round(v / groups) for v in buf[:7]],
-      "= fetch d1 | gather d0 | wait ring | store d0 | advance+fetch next | gather+store d1 | fence+arrive+rotate")
+for label, fn in [("forward", lambda: conv3p_forward(plan, pr["input"], pr["filter"])),
+                  ("backward", lambda: conv3p_backward(plan, pr["grad_out"], pr["input"], pr["filter"]))]:
+    L.conv3p_set_engine(64 + 32)
+    L.conv3p_debug_phase_cycles(buf)
+    fn(); torch.cuda.synchronize()
+    L.conv3p_debug_phase_cycles(buf)
+    L.conv3p_set_engine(0)
+    tiles = (B * N + 383) // 384
+    v = [x / tiles for x in buf]
+    print(f"{label}: k_gather_mma2 cycles per CTA (thread 0): prologue {v[0]:.0f} | producer loop {v[1]:.0f} | "
+          f"wait last MMA {v[2]:.0f} | epilogue {v[3]:.0f} || in loop: item fetch {v[4]:.0f} | gather 0 {v[5]:.0f} | "
+          f"ring wait {v[6]:.0f} | stores+rep 1+arrive {v[7]:.0f}")
+# first-generation kernels for comparison
+L.conv3p_set_engine(128)
+for fn, label in [(lambda: conv3p_forward(plan, pr["input"], pr["filter"]), "fwd"),
+                  (lambda: conv3p_backward(plan, pr["grad_out"], pr["input"], pr["filter"]), "bwd")]:
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): fn()
+    e1.record(); torch.cuda.synchronize()
+    print(f"{'gen1':10s} {label:7s} {e0.elapsed_time(e1)/5:.3f} ms")
 L.conv3p_set_engine(0)
