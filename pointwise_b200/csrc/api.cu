@@ -267,6 +267,10 @@ size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
     const size_t t = backward_filter_tc_scratch_bytes(geom, Cin, Cout);
     if (t > filt) filt = t;
   }
+  if (backward_filter2_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
+    const size_t t = backward_filter2_scratch_bytes(geom, Cin, Cout);
+    if (t > filt) filt = t;
+  }
   return weight_panel_bytes(Cin, Cout) + tc_items_bytes(geom, Cin, Cout) + filt + 256;
 }
 
@@ -316,7 +320,10 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
     if (!input && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
     const size_t wpb = weight_panel_bytes(Cin, Cout) + tc_items_bytes(geom, Cin, Cout);
     if (!scratch || scratch_bytes < wpb) return CONV3P_ERR_BUFFER_TOO_SMALL;
-    if (engine() != 1 && backward_filter_tc_supported(geom->N, geom->pair_capacity, Cin, Cout))
+    if (engine() != 1 && !(engine() & 128) && backward_filter2_supported(geom->N, geom->pair_capacity, Cin, Cout))
+      st = launch_backward_filter2(geom, v, grad_output, input, Cin, Cout, grad_filter,
+                                   static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);
+    else if (engine() != 1 && backward_filter_tc_supported(geom->N, geom->pair_capacity, Cin, Cout))
       st = launch_backward_filter_tc(geom, v, grad_output, input, Cin, Cout, grad_filter,
                                      static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);
     else if (engine() != 3 && small_backward_filter_supported(Cin, Cout))

@@ -79,6 +79,19 @@ int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* in
 // second-generation gather + MMA kernel (gather_mma2.cu); engine bit 128 selects the first generation instead
 bool gather_mma2_supported(int N, long long capacity, int Csrc, int Nout);
 size_t gather_mma2_scratch_bytes(const conv3p_geom_t* g);  // work-item lists of one launch
+// Work-item lists of the tensor-core kernels (k_group_items): per sub-tile of `rows` voxel-sorted points and per
+// kernel cell, `rows` items (list position, row | members << 8) compacted by population class.
+struct GroupItems {
+  uint2* items;     // [subtiles][27][rows]
+  int* nnz;         // [subtiles][27] non-empty rows of the group
+  int* rowid;       // [subtiles*rows] tensor row of every sorted position (-1 pad, -2-row: incomplete list)
+  unsigned* mask;   // [subtiles] bit f: group f has members
+  long long subtiles;
+};
+size_t group_items_bytes(long long pts, int rows);
+GroupItems carve_group_items(void* scratch, long long pts, int rows);
+int launch_group_items(const conv3p_geom_t* g, const PlanView& v, bool backward_lists, int rows,
+                       const GroupItems& gi, cudaStream_t stream);
 int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* src, const void* wp, int Csrc,
                        int Nout, float* out, bool weighted, void* scratch, size_t scratch_bytes, const char* name,
                        cudaStream_t stream);
@@ -90,6 +103,13 @@ size_t backward_filter_tc_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cou
 int launch_backward_filter_tc(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
                               const float* input, int Cin, int Cout, float* grad_filter, void* scratch,
                               size_t scratch_bytes, cudaStream_t stream);
+
+// second-generation weight-gradient kernel (backward_filter2.cu)
+bool backward_filter2_supported(int N, long long capacity, int Cin, int Cout);
+size_t backward_filter2_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout);
+int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const float* grad_out, const float* input,
+                            int Cin, int Cout, float* grad_filter, void* scratch, size_t scratch_bytes,
+                            cudaStream_t stream);
 
 // warp-per-point fp32 engine for the reference models' small channel counts (3, 9, 13, 36)
 bool small_channels_supported(int Cin, int Cout);

@@ -24,6 +24,7 @@
 // allocator, NPW+2 = item-list loader.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_gather2.cuh"
 
 namespace c3p {
 
@@ -55,156 +56,83 @@ struct G2Args {
 // in the loop: item fetch | first gather | wait for a free ring stage | stores + second repetition + arrive
 __device__ unsigned long long g2_phase_cycles[8];
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-// acc += w * v on both halves of a float4 (two FFMA2)
-__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
-  const float2 ww = make_float2(w, w);
-  const float2 lo = __ffma2_rn(ww, make_float2(v.x, v.y), make_float2(acc.x, acc.y));
-  const float2 hi = __ffma2_rn(ww, make_float2(v.z, v.w), make_float2(acc.z, acc.w));
-  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-
-struct G2Item {
-  uint32_t pos;   // position of the cell's first entry in the list arrays
-  int p;          // row of the sub-tile (0..127)
-  int n;          // members (0: store zeros)
-  float inv;      // 1 / n (unweighted lists; MUFU reciprocal, within 1 ulp)
-  int ids;        // lane l8: row id of entry l8 of the list (prefetched)
-  float w;        // lane l8: its weight (WEIGHTED)
-};
-
-template <bool WEIGHTED>
-__device__ __forceinline__ void g2_prefetch(G2Item& it, const int* __restrict__ rows,
-                                            const float* __restrict__ weights, int m0, int l8,
-                                            unsigned max_row) {
-  // select on the ADDRESS: nothing consumes the loaded values until the item is gathered
-  const uint32_t at = it.n > 0 ? it.pos + (uint32_t)min(m0 + l8, it.n - 1) : 0u;
-  it.ids = (int)min((unsigned)__ldg(rows + at), max_row);
-  if (WEIGHTED) it.w = __ldg(weights + at);
-}
-
-// acc[kc] = sum_m w_m * src[list[m], col + kc*32 + l8*4 .. +4].  Called by all 32 lanes; n is uniform inside a
-// quarter-warp and the trip count is made warp-uniform (the id broadcast is a shuffle).
-template <int NKC, bool WEIGHTED>
-__device__ __forceinline__ void g2_gather(float4 (&acc)[NKC], G2Item& it, int nmax,
-                                          const float* __restrict__ src, int Csrc, int col,
-                                          const int* __restrict__ rows, const float* __restrict__ weights,
-                                          int l8, unsigned max_row) {
-#pragma unroll
-  for (int kc = 0; kc < NKC; ++kc) acc[kc] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* base = src + col + l8 * 4;
-  for (int m0 = 0; m0 < nmax; m0 += 4) {
-    if (m0 && !(m0 & 7)) g2_prefetch<WEIGHTED>(it, rows, weights, m0, l8, max_row);
-    float4 v[4][NKC];
-    float wv[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int id = __shfl_sync(C3P_FULL_MASK, it.ids, (m0 + m) & 7, 8);
-      float w = it.inv;
-      if (WEIGHTED) w = __shfl_sync(C3P_FULL_MASK, it.w, (m0 + m) & 7, 8);
-      wv[m] = (m0 + m < it.n) ? w : 0.f;
-      const float* p = base + (size_t)id * Csrc;
-#pragma unroll
-      for (int kc = 0; kc < NKC; ++kc) v[m][kc] = ldg4(p + kc * PANEL_K);
-    }
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-      for (int kc = 0; kc < NKC; ++kc) fma4(acc[kc], wv[m], v[m][kc]);
-  }
-}
-
-__device__ __forceinline__ void g2_store_split(unsigned char* dst, const float4& v) {
-  const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-  const float2 l0 = __fadd2_rn(make_float2(v.x, v.y), make_float2(-h.x, -h.y));
-  const float2 l1 = __fadd2_rn(make_float2(v.z, v.w), make_float2(-h.z, -h.w));
-  *reinterpret_cast<float4*>(dst) = h;
-  *reinterpret_cast<float4*>(dst + 128 * PANEL_ROW_BYTES) = make_float4(l0.x, l0.y, l1.x, l1.y);
-}
-
 // ---- pre-pass: compacted work-item lists per (sub-tile, cell) group ---------------------------------------------
-// One warp per sub-tile of 128 voxel-sorted points; lane l owns rows l, l+32, l+64, l+96 and carries their list
-// positions across the 27 cells.  Within a group the rows are ranked by population class (0: more than 8 members,
-// 1: 5..8, 2: 1..4, 3: empty) with ballots, so item index = class base + rank inside the class.
-constexpr int GI_WARPS = 8;
-
-__global__ void __launch_bounds__(GI_WARPS * 32)
+// One CTA per sub-tile of ROWS voxel-sorted points, one thread per row.  Within a group the rows are ranked by
+// population class (0: more than 8 members, 1: 5..8, 2: 1..4, 3: empty): warp ballots give the rank inside the
+// warp, per-warp class counts (one byte each) go through shared memory, so item index = class base + rank.
+// The 27 lists of the sub-tile are staged in shared memory and written out with coalesced 16-byte stores.
+template <int ROWS>
+__global__ void __launch_bounds__(ROWS)
 k_group_items(const int* __restrict__ cnt, const long long* __restrict__ begin, const int* __restrict__ len,
               const float4* __restrict__ sorted_xyzi, long long total_points, long long capacity, int N,
-              long long subtiles, uint2* __restrict__ g_items, int* __restrict__ g_nnz, int* __restrict__ g_rowid) {
-  const long long sub = (long long)blockIdx.x * GI_WARPS + (threadIdx.x >> 5);
-  if (sub >= subtiles) return;
-  const int lane = threadIdx.x & 31;
+              uint2* __restrict__ g_items, int* __restrict__ g_nnz, int* __restrict__ g_rowid,
+              unsigned* __restrict__ g_mask) {
+  constexpr int NW = ROWS / 32;
+  __shared__ uint2 stage[C3P_NCELL * ROWS];
+  __shared__ uint32_t wcls[C3P_NCELL][NW];  // per warp: rows of class 0..3, one byte each
+  const long long sub = blockIdx.x;
+  const int r = threadIdx.x, lane = r & 31, warp = r >> 5;
   const unsigned lt = lanemask_lt();
-  uint32_t pos[4];
-  const int* crow[4];
-  bool ok[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long s = sub * 128 + lane + 32 * i;
-    int row = -1;
-    pos[i] = 0;
-    ok[i] = false;
-    crow[i] = cnt;
-    if (s < total_points) {
-      const int b = (int)(s / N);
-      row = b * N + __float_as_int(sorted_xyzi[s].w);
-      const long long bg = begin[row];
-      ok[i] = bg + len[row] <= capacity;
-      pos[i] = (uint32_t)bg;
-      crow[i] = cnt + (size_t)row * C3P_NCELL;
-      if (!ok[i]) row = -2 - row;  // incomplete list: the main kernel poisons this point's output
-    }
-    g_rowid[s] = row;
+  const long long s = sub * ROWS + r;
+  int row = -1;
+  uint32_t pos = 0;
+  bool ok = false;
+  const int* crow = cnt;
+  if (s < total_points) {
+    const int b = (int)(s / N);
+    row = b * N + __float_as_int(sorted_xyzi[s].w);
+    const long long bg = begin[row];
+    ok = bg + len[row] <= capacity;
+    pos = (uint32_t)bg;
+    crow = cnt + (size_t)row * C3P_NCELL;
+    if (!ok) row = -2 - row;  // incomplete list: the consumer poisons this point's output
   }
-  uint2* out = g_items + sub * C3P_NCELL * 128;
-  constexpr int FB = 9;  // cells per batch of count loads
-  for (int f0 = 0; f0 < C3P_NCELL; f0 += FB) {
-    int c[FB][4];
+  g_rowid[s] = row;
+  int c[C3P_NCELL];
 #pragma unroll
-    for (int j = 0; j < FB; ++j)
+  for (int f = 0; f < C3P_NCELL; ++f) c[f] = ok ? __ldg(crow + f) : 0;
+  uint32_t rank[C3P_NCELL];  // class | rank inside the warp << 8
 #pragma unroll
-      for (int i = 0; i < 4; ++i) c[j][i] = ok[i] ? __ldg(crow[i] + f0 + j) : 0;
+  for (int f = 0; f < C3P_NCELL; ++f) {
+    const int n = c[f];
+    const int cls = n > 8 ? 0 : (n > 4 ? 1 : (n > 0 ? 2 : 3));
+    uint32_t packed = 0, mine = 0;
 #pragma unroll
-    for (int j = 0; j < FB; ++j) {
-      unsigned m[4][4];
-      int cls[4];
+    for (int k = 0; k < 4; ++k) {
+      const unsigned m = __ballot_sync(C3P_FULL_MASK, cls == k);
+      packed |= (uint32_t)__popc(m) << (8 * k);   // at most 32 per warp and class
+      if (cls == k) mine = (uint32_t)__popc(m & lt);
+    }
+    rank[f] = (uint32_t)cls | (mine << 8);
+    if (lane == 0) wcls[f][warp] = packed;
+  }
+  __syncthreads();
+  unsigned mask = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int n = c[j][i];
-        cls[i] = n > 8 ? 0 : (n > 4 ? 1 : (n > 0 ? 2 : 3));
+  for (int f = 0; f < C3P_NCELL; ++f) {
+    const int cls = (int)(rank[f] & 255u);
+    int idx = (int)(rank[f] >> 8), nonempty = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) m[k][i] = __ballot_sync(C3P_FULL_MASK, cls[i] == k);
-      }
-      int base[4];
-      int run = 0;
+    for (int w = 0; w < NW; ++w) {
+      const uint32_t pk = wcls[f][w];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        base[k] = run;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) run += __popc(m[k][i]);
+        const int v = (int)((pk >> (8 * k)) & 255u);
+        if (k < cls || (k == cls && w < warp)) idx += v;
+        if (k < 3) nonempty += v;
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int idx = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (cls[i] == k) {
-            idx = base[k] + __popc(m[k][i] & lt);
-#pragma unroll
-            for (int i2 = 0; i2 < 4; ++i2)
-              if (i2 < i) idx += __popc(m[k][i2]);
-          }
-        }
-        out[(f0 + j) * 128 + idx] = make_uint2(pos[i], (uint32_t)(lane + 32 * i) | ((uint32_t)c[j][i] << 8));
-        pos[i] += (uint32_t)c[j][i];
-      }
-      if (lane == 0) g_nnz[sub * C3P_NCELL + f0 + j] = base[3];  // rows of classes 0..2
     }
+    stage[f * ROWS + idx] = make_uint2(pos, (uint32_t)r | ((uint32_t)c[f] << 8));
+    pos += (uint32_t)c[f];
+    if (nonempty) mask |= 1u << f;
+    if (r == f) g_nnz[sub * C3P_NCELL + f] = nonempty;
   }
+  if (r == 0) g_mask[sub] = mask;
+  __syncthreads();
+  const uint4* src = reinterpret_cast<const uint4*>(stage);
+  uint4* dst = reinterpret_cast<uint4*>(g_items + sub * C3P_NCELL * ROWS);
+  for (int e = r; e < C3P_NCELL * ROWS / 2; e += ROWS) dst[e] = src[e];
 }
-
 
 template <int NKC, bool WEIGHTED>
 __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
@@ -303,7 +231,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
       G2_PHASE(4);
       const int col = hc * NKC * PANEL_K;
       float4 acc[NKC];
-      g2_gather<NKC, WEIGHTED>(acc, c0, warp_max(c0.n), a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
+      g2_gather<NKC, 4, WEIGHTED>(acc, c0, warp_max(c0.n), a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
       G2_PHASE(5);
       // the ring stages of this group must have been drained by the tensor core
       unsigned char* stage[NKC];
@@ -321,16 +249,16 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
       {
         const uint32_t o = panel_chunk_offset(c0.p, l8);
 #pragma unroll
-        for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, acc[kc]);
+        for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, 128 * PANEL_ROW_BYTES, acc[kc]);
       }
       const int nmax1 = warp_max(c1.n);
       if (nmax1 > 0)
-        g2_gather<NKC, WEIGHTED>(acc, c1, nmax1, a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
+        g2_gather<NKC, 4, WEIGHTED>(acc, c1, nmax1, a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
       {
         const uint32_t o = panel_chunk_offset(c1.p, l8);
         if (nmax1 > 0) {
 #pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, acc[kc]);
+          for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, 128 * PANEL_ROW_BYTES, acc[kc]);
         } else {
           const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -552,13 +480,47 @@ bool gather_mma2_supported(int N, long long capacity, int Csrc, int Nout) {
   return g2_config(N, capacity, Csrc, Nout, &c);
 }
 
-// scratch of one launch: [items | nnz | rowid]
-static size_t g2_items_bytes(long long subtiles) { return align_up((size_t)subtiles * C3P_NCELL * 128 * sizeof(uint2)); }
-static size_t g2_nnz_bytes(long long subtiles) { return align_up((size_t)subtiles * C3P_NCELL * sizeof(int)); }
-size_t gather_mma2_scratch_bytes(const conv3p_geom_t* g) {
-  const long long subtiles = ((long long)g->B * g->N + 127) / 128;
-  return g2_items_bytes(subtiles) + g2_nnz_bytes(subtiles) + align_up((size_t)subtiles * 128 * sizeof(int));
+// scratch of one item-list set: [items | nnz | rowid | mask]
+size_t group_items_bytes(long long pts, int rows) {
+  const long long subtiles = (pts + rows - 1) / rows;
+  return align_up((size_t)subtiles * C3P_NCELL * rows * sizeof(uint2)) +
+         align_up((size_t)subtiles * C3P_NCELL * sizeof(int)) + align_up((size_t)subtiles * rows * sizeof(int)) +
+         align_up((size_t)subtiles * sizeof(unsigned));
 }
+
+GroupItems carve_group_items(void* scratch, long long pts, int rows) {
+  const long long subtiles = (pts + rows - 1) / rows;
+  char* sp = static_cast<char*>(scratch);
+  GroupItems gi;
+  gi.subtiles = subtiles;
+  gi.items = reinterpret_cast<uint2*>(sp); sp += align_up((size_t)subtiles * C3P_NCELL * rows * sizeof(uint2));
+  gi.nnz = reinterpret_cast<int*>(sp); sp += align_up((size_t)subtiles * C3P_NCELL * sizeof(int));
+  gi.rowid = reinterpret_cast<int*>(sp); sp += align_up((size_t)subtiles * rows * sizeof(int));
+  gi.mask = reinterpret_cast<unsigned*>(sp);
+  return gi;
+}
+
+int launch_group_items(const conv3p_geom_t* g, const PlanView& v, bool backward_lists, int rows,
+                       const GroupItems& gi, cudaStream_t stream) {
+  const long long pts = (long long)g->B * g->N;
+  if (pts == 0) return CONV3P_OK;
+  const int* cnt = backward_lists ? v.bwd_count : v.count_table;
+  {
+    LaunchTimer timer_("k_group_items", stream);
+    if (rows == 128)
+      k_group_items<128><<<(unsigned)gi.subtiles, 128, 0, stream>>>(cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts,
+                                                                    g->pair_capacity, g->N, gi.items, gi.nnz,
+                                                                    gi.rowid, gi.mask);
+    else
+      k_group_items<64><<<(unsigned)gi.subtiles, 64, 0, stream>>>(cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts,
+                                                                  g->pair_capacity, g->N, gi.items, gi.nnz, gi.rowid,
+                                                                  gi.mask);
+  }
+  C3P_LAUNCH_CHECK("k_group_items");
+  return CONV3P_OK;
+}
+
+size_t gather_mma2_scratch_bytes(const conv3p_geom_t* g) { return group_items_bytes((long long)g->B * g->N, 128); }
 
 int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* src, const void* wp, int Csrc,
                        int Nout, float* out, bool weighted, void* scratch, size_t scratch_bytes, const char* name,
@@ -568,23 +530,17 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
   if (!g2_config(g->N, g->pair_capacity, Csrc, Nout, &c, pts)) return CONV3P_ERR_UNSUPPORTED;
   if (pts == 0) return CONV3P_OK;
   if (!scratch || scratch_bytes < gather_mma2_scratch_bytes(g)) return CONV3P_ERR_BUFFER_TOO_SMALL;
-  const long long subtiles = (pts + 127) / 128;
-  char* sp = static_cast<char*>(scratch);
-  uint2* g_items = reinterpret_cast<uint2*>(sp);
-  int* g_nnz = reinterpret_cast<int*>(sp + g2_items_bytes(subtiles));
-  int* g_rowid = reinterpret_cast<int*>(sp + g2_items_bytes(subtiles) + g2_nnz_bytes(subtiles));
+  const GroupItems gi = carve_group_items(scratch, pts, 128);
+  const long long subtiles = gi.subtiles;
   {
-    LaunchTimer timer_("k_group_items", stream);
-    k_group_items<<<(unsigned)((subtiles + GI_WARPS - 1) / GI_WARPS), GI_WARPS * 32, 0, stream>>>(
-        weighted ? v.bwd_count : v.count_table, v.pair_begin, v.pair_len, v.sorted_xyzi, pts, g->pair_capacity,
-        g->N, subtiles, g_items, g_nnz, g_rowid);
+    const int st = launch_group_items(g, v, weighted, 128, gi, stream);
+    if (st) return st;
   }
-  C3P_LAUNCH_CHECK("k_group_items");
   G2Args a{};
   a.src = src; a.wp = static_cast<const unsigned char*>(wp); a.out = out;
   a.rows = weighted ? v.bwd_row : v.pair_row;
   a.weights = weighted ? v.bwd_weight : nullptr;
-  a.g_items = g_items; a.g_nnz = g_nnz; a.g_rowid = g_rowid;
+  a.g_items = gi.items; a.g_nnz = gi.nnz; a.g_rowid = gi.rowid;
   a.total_points = pts; a.subtiles = subtiles;
   a.N = g->N; a.Csrc = Csrc; a.Nout = Nout;
   a.nkb = c.nkb; a.T = c.T; a.NAS = c.NAS; a.NWU = c.NWU;
