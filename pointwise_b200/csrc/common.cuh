@@ -86,6 +86,7 @@ struct GroupItems {
   int* nnz;         // [subtiles][27] non-empty rows of the group
   int* rowid;       // [subtiles*rows] tensor row of every sorted position (-1 pad, -2-row: incomplete list)
   unsigned* mask;   // [subtiles] bit f: group f has members
+  unsigned* counter;  // one word, zeroed by k_group_items: chunk counter of the consumer's tile scheduler
   long long subtiles;
 };
 size_t group_items_bytes(long long pts, int rows);

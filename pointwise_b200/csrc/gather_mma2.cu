@@ -47,6 +47,7 @@ struct G2Args {
   const uint2* g_items;     // [subtiles][27][128] work items (k_group_items)
   const int* g_nnz;         // [subtiles][27] non-empty rows of the group
   const int* g_rowid;       // [subtiles*128] output row of every sorted position (-1 pad, -2-row poisoned)
+  unsigned* counter;        // chunk counter of the dynamic tile scheduler (zeroed by k_group_items)
   long long total_points, subtiles;
   int N, Csrc, Nout, nkb, T, NAS, NWU;
   int debug;  // bit 32: accumulate the phase timers below
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(ROWS)
 k_group_items(const int* __restrict__ cnt, const long long* __restrict__ begin, const int* __restrict__ len,
               const float4* __restrict__ sorted_xyzi, long long total_points, long long capacity, int N,
               uint2* __restrict__ g_items, int* __restrict__ g_nnz, int* __restrict__ g_rowid,
-              unsigned* __restrict__ g_mask) {
+              unsigned* __restrict__ g_mask, unsigned* __restrict__ g_counter) {
   constexpr int NW = ROWS / 32;
   __shared__ uint2 stage[C3P_NCELL * ROWS];
   __shared__ uint32_t wcls[C3P_NCELL][NW];  // per warp: rows of class 0..3, one byte each
@@ -128,6 +129,7 @@ k_group_items(const int* __restrict__ cnt, const long long* __restrict__ begin, 
     if (r == f) g_nnz[sub * C3P_NCELL + f] = nonempty;
   }
   if (r == 0) g_mask[sub] = mask;
+  if (r == 0 && sub == 0) *g_counter = 0u;
   __syncthreads();
   const uint4* src = reinterpret_cast<const uint4*>(stage);
   uint4* dst = reinterpret_cast<uint4*>(g_items + sub * C3P_NCELL * ROWS);
@@ -137,27 +139,24 @@ k_group_items(const int* __restrict__ cnt, const long long* __restrict__ begin, 
 template <int NKC, bool WEIGHTED>
 __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int T = a.T, Nout = a.Nout, NAS = a.NAS, NWU = a.NWU;
-  const int PT = T * 128;
+  const int Nout = a.Nout, NAS = a.NAS, NWU = a.NWU;
   const uint32_t unit_bytes = (uint32_t)Nout * PANEL_ROW_BYTES;       // hi (or lo) half of a weight panel
   unsigned char* a_base = smem;                                       // NAS stages
   unsigned char* w_base = a_base + (size_t)NAS * G2_A_STAGE;          // NWU units
   uint2* items = reinterpret_cast<uint2*>(w_base + (size_t)NWU * unit_bytes);  // [NIS][128]
-  int* rowid = reinterpret_cast<int*>(items + G2_NIS * 128);          // [PT]
+  int* rowid = reinterpret_cast<int*>(items + G2_NIS * 128);          // [Tmax * 128]
   __shared__ uint64_t a_full[G2_MAX_NAS], a_empty[G2_MAX_NAS], w_full[G2_MAX_NWU], w_empty[G2_MAX_NWU],
       it_full[G2_NIS], it_empty[G2_NIS], acc_full;
   __shared__ uint32_t tmem_slot;
-  __shared__ unsigned active[C3P_NCELL];  // bit t: sub-tile t has members in cell f
+  __shared__ unsigned active[C3P_NCELL];  // bit t: sub-tile t of the chunk has members in cell f
   __shared__ int hdr[G2_NIS];             // K batch of the group in the slot, or G2_END
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long s0 = (long long)blockIdx.x * PT;
   const bool timed = (a.debug & 32) && tid == 0;
   long long tk = timed ? clock64() : 0;
-  unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define G2_PHASE(i) do { if (timed) { const long long t_ = clock64(); ph[i] += (unsigned long long)(t_ - tk); tk = t_; } } while (0)
+  unsigned ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define G2_PHASE(i) do { if (timed) { const long long t_ = clock64(); ph[i] += (unsigned)(t_ - tk); tk = t_; } } while (0)
 
-  if (tid < C3P_NCELL) active[tid] = 0;
   if (warp == G2_NPW && lane == 0) {
     for (int i = 0; i < NAS; ++i) {
       mbar_init(&a_full[i], G2_NPW);
@@ -175,262 +174,307 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
     mbar_fence_init();
   }
   if (warp == G2_NPW + 1) tmem_alloc(&tmem_slot, 512);
-  __syncthreads();
-  // ---- output rows of the tile and which (cell, sub-tile) groups have members at all ---------------------------
-  const long long sub0 = (long long)blockIdx.x * T;
-  for (int p = tid; p < PT; p += G2_THREADS)
-    rowid[p] = (sub0 + (p >> 7) < a.subtiles) ? __ldg(a.g_rowid + s0 + p) : -1;
-  if (tid < C3P_NCELL * T) {
-    const int t = tid / C3P_NCELL, f = tid - t * C3P_NCELL;
-    if (sub0 + t < a.subtiles && __ldg(a.g_nnz + (sub0 + t) * C3P_NCELL + f) > 0) atomicOr(&active[f], 1u << t);
-  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const unsigned max_row = (unsigned)(a.total_points - 1);
-  G2_PHASE(0);
 
-  if (warp < G2_NPW) {
-    // =========================== producers: gather -> mean -> hi/lo -> operand panels ===================
-    // Quarter-warp q serves items (q + 4g) mod 64 and 64 + that of group g; lane l8 owns one 16-byte chunk of
-    // the row segment.  Software-pipelined: the item and the list ids of the next group are fetched before
-    // the rows of the current group are gathered.
-    const int q = warp * 4 + (lane >> 3);
-    const int l8 = lane & 7;
-    auto read_items = [&](int g_, G2Item& i0, G2Item& i1) -> int {
-      const int slot = g_ & (G2_NIS - 1);
-      mbar_wait(&it_full[slot], (uint32_t)((g_ / G2_NIS) & 1));
-      const int h = hdr[slot];
-      const int e = (q + 4 * g_) & 63;
-      const uint2 u0 = items[slot * 128 + e], u1 = items[slot * 128 + 64 + e];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&it_empty[slot]);
-      const bool live = h != G2_END;
-      i0.pos = u0.x; i0.p = (int)(u0.y & 255u); i0.n = live ? (int)(u0.y >> 8) : 0;
-      i1.pos = u1.x; i1.p = (int)(u1.y & 255u); i1.n = live ? (int)(u1.y >> 8) : 0;
-      i0.inv = WEIGHTED ? 0.f : __fdividef(1.f, (float)i0.n);
-      i1.inv = WEIGHTED ? 0.f : __fdividef(1.f, (float)i1.n);
-      i0.w = 0.f; i1.w = 0.f;
-      g2_prefetch<WEIGHTED>(i0, a.rows, a.weights, 0, l8, max_row);
-      g2_prefetch<WEIGHTED>(i1, a.rows, a.weights, 0, l8, max_row);
-      return h;
-    };
-    auto warp_max = [&](int n) -> int {
-      n = max(n, __shfl_xor_sync(C3P_FULL_MASK, n, 8));
-      return max(n, __shfl_xor_sync(C3P_FULL_MASK, n, 16));
-    };
-    int g = 0, aslot = 0;
-    uint32_t awrap = 0;  // times the ring wrapped before stage `aslot`
-    G2Item c0, c1;
-    int hc = read_items(0, c0, c1);
-    long long tl = timed ? clock64() : 0;
-    while (hc != G2_END) {
-      G2Item n0, n1;
-      const int hn = read_items(g + 1, n0, n1);
-      G2_PHASE(4);
-      const int col = hc * NKC * PANEL_K;
-      float4 acc[NKC];
-      g2_gather<NKC, 4, WEIGHTED>(acc, c0, warp_max(c0.n), a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
-      G2_PHASE(5);
-      // the ring stages of this group must have been drained by the tensor core
-      unsigned char* stage[NKC];
-      {
-        int sl = aslot;
-        uint32_t wr = awrap;
-#pragma unroll
-        for (int kc = 0; kc < NKC; ++kc) {
-          if (wr >= 1) mbar_wait(&a_empty[sl], (wr - 1) & 1u);
-          stage[kc] = a_base + (size_t)sl * G2_A_STAGE;
-          if (++sl == NAS) { sl = 0; ++wr; }
-        }
-      }
-      G2_PHASE(6);
-      {
-        const uint32_t o = panel_chunk_offset(c0.p, l8);
-#pragma unroll
-        for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, 128 * PANEL_ROW_BYTES, acc[kc]);
-      }
-      const int nmax1 = warp_max(c1.n);
-      if (nmax1 > 0)
-        g2_gather<NKC, 4, WEIGHTED>(acc, c1, nmax1, a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
-      {
-        const uint32_t o = panel_chunk_offset(c1.p, l8);
-        if (nmax1 > 0) {
-#pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, 128 * PANEL_ROW_BYTES, acc[kc]);
-        } else {
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  // Persistent CTA with a dynamic scheduler: chunks of sub-tiles (one TMEM accumulator per sub-tile) are claimed
+  // from a global counter.  Chunk k maps to a fixed range: chunks of Tmax sub-tiles first, then -- for the last
+  // few sub-tiles per CTA -- chunks of 2 and of 1, so that the tail of the launch is short although the work per
+  // sub-tile varies a lot (dense floors and walls against sparse clutter).
+  __shared__ long long s_sub0;
+  __shared__ int s_T;
+  const long long G = gridDim.x;
+  const int Tmax = a.T;
+  const long long n_big = a.subtiles > 6 * G ? (a.subtiles - 6 * G) / Tmax : 0;         // chunks of Tmax
+  const long long r1 = a.subtiles - n_big * Tmax;
+  const long long n_mid = (Tmax >= 2 && r1 > 2 * G) ? (r1 - 2 * G) / 2 : 0;                            // chunks of 2
+  const long long n_one = r1 - n_mid * 2;                                               // chunks of 1
+  auto claim = [&]() {
+    const long long k = (long long)atomicAdd(a.counter, 1u);
+    long long sub = 0;
+    int T = 0;
+    if (k < n_big) { sub = k * Tmax; T = Tmax; }
+    else if (k < n_big + n_mid) { sub = n_big * Tmax + (k - n_big) * 2; T = 2; }
+    else if (k < n_big + n_mid + n_one) { sub = n_big * Tmax + n_mid * 2 + (k - n_big - n_mid); T = 1; }
+    s_sub0 = sub;
+    s_T = T;
+  };
+  if (tid == 0) claim();
+  __syncthreads();
+
+  // role state that lives across chunks
+  const int q = warp * 4 + (lane >> 3);
+  const int l8 = lane & 7;
+  // (one register set shared by the roles: a thread only ever plays one of them)
+  int st_a = 0, st_b = 0;
+  uint32_t st_c = 0, st_d = 0;
+  int& p_g = st_a; int& p_aslot = st_b; uint32_t& p_awrap = st_c;                          // producers
+  int& m_aslot = st_a; int& m_wslot = st_b; uint32_t& m_aphase = st_c; uint32_t& m_wphase = st_d;  // MMA issuer
+  int& l_slot = st_a; uint32_t& l_wrap = st_c;                                             // weight loader
+  int& i_g = st_a;                                                                         // item-list loader
+  int chunk = 0;
+
+  for (;; ++chunk) {
+    const long long sub0 = s_sub0;
+    const int T = s_T;
+    if (T == 0) break;
+    const int PT = T * 128;
+    // ---- output rows of the chunk and which (cell, sub-tile) groups have members at all ----------------------------
+    for (int p = tid; p < PT; p += G2_THREADS) rowid[p] = __ldg(a.g_rowid + sub0 * 128 + p);
+    if (tid < C3P_NCELL) {
+      unsigned m = 0;
+      for (int t = 0; t < T; ++t)
+        if (__ldg(a.g_nnz + (sub0 + t) * C3P_NCELL + tid) > 0) m |= 1u << t;
+      active[tid] = m;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    G2_PHASE(0);
+    if (tid == 0) claim();  // next chunk; everybody has read this chunk's range, the answer is read after the end barrier
+
+    if (warp < G2_NPW) {
+      // =========================== producers: gather -> mean -> hi/lo -> operand panels ===================
+      // Quarter-warp q serves items (q + 4g) mod 64 and 64 + that of group g; lane l8 owns one 16-byte chunk of
+      // the row segment.  Software-pipelined: the item and the list ids of the next group are fetched before
+      // the rows of the current group are gathered.
+      auto read_items = [&](int g_, G2Item& i0, G2Item& i1) -> int {
+        const int slot = g_ & (G2_NIS - 1);
+        mbar_wait(&it_full[slot], (uint32_t)((g_ / G2_NIS) & 1));
+        const int h = hdr[slot];
+        const int e = (q + 4 * g_) & 63;
+        const uint2 u0 = items[slot * 128 + e], u1 = items[slot * 128 + 64 + e];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&it_empty[slot]);
+        const bool live = h != G2_END;
+        i0.pos = u0.x; i0.p = (int)(u0.y & 255u); i0.n = live ? (int)(u0.y >> 8) : 0;
+        i1.pos = u1.x; i1.p = (int)(u1.y & 255u); i1.n = live ? (int)(u1.y >> 8) : 0;
+        i0.inv = WEIGHTED ? 0.f : __fdividef(1.f, (float)i0.n);
+        i1.inv = WEIGHTED ? 0.f : __fdividef(1.f, (float)i1.n);
+        i0.w = 0.f; i1.w = 0.f;
+        g2_prefetch<WEIGHTED>(i0, a.rows, a.weights, 0, l8, max_row);
+        g2_prefetch<WEIGHTED>(i1, a.rows, a.weights, 0, l8, max_row);
+        return h;
+      };
+      auto warp_max = [&](int n) -> int {
+        n = max(n, __shfl_xor_sync(C3P_FULL_MASK, n, 8));
+        return max(n, __shfl_xor_sync(C3P_FULL_MASK, n, 16));
+      };
+      G2Item c0, c1;
+      int hc = read_items(p_g, c0, c1);
+      long long tl = timed ? clock64() : 0;
+      if (timed) tk = tl;
+      while (hc != G2_END) {
+        G2Item n0, n1;
+        const int hn = read_items(p_g + 1, n0, n1);
+        G2_PHASE(4);
+        const int col = hc * NKC * PANEL_K;
+        float4 acc[NKC];
+        g2_gather<NKC, 4, WEIGHTED>(acc, c0, warp_max(c0.n), a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
+        G2_PHASE(5);
+        // the ring stages of this group must have been drained by the tensor core
+        unsigned char* stage[NKC];
+        {
+          int sl = p_aslot;
+          uint32_t wr = p_awrap;
 #pragma unroll
           for (int kc = 0; kc < NKC; ++kc) {
-            *reinterpret_cast<float4*>(stage[kc] + o) = z;
-            *reinterpret_cast<float4*>(stage[kc] + o + 128 * PANEL_ROW_BYTES) = z;
+            if (wr >= 1) mbar_wait(&a_empty[sl], (wr - 1) & 1u);
+            stage[kc] = a_base + (size_t)sl * G2_A_STAGE;
+            if (++sl == NAS) { sl = 0; ++wr; }
           }
         }
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        int sl = aslot;
+        G2_PHASE(6);
+        {
+          const uint32_t o = panel_chunk_offset(c0.p, l8);
 #pragma unroll
-        for (int kc = 0; kc < NKC; ++kc) {
-          mbar_arrive(&a_full[sl]);
-          if (++sl == NAS) sl = 0;
+          for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, 128 * PANEL_ROW_BYTES, acc[kc]);
         }
-      }
+        const int nmax1 = warp_max(c1.n);
+        if (nmax1 > 0)
+          g2_gather<NKC, 4, WEIGHTED>(acc, c1, nmax1, a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
+        {
+          const uint32_t o = panel_chunk_offset(c1.p, l8);
+          if (nmax1 > 0) {
 #pragma unroll
-      for (int kc = 0; kc < NKC; ++kc)
-        if (++aslot == NAS) { aslot = 0; ++awrap; }
-      ++g;
-      c0 = n0; c1 = n1; hc = hn;
-      G2_PHASE(7);
-    }
-    if (timed) { tk = clock64(); ph[1] = (unsigned long long)(tk - tl); }
-    // =========================== epilogue: TMEM -> registers -> global ==============================
-    mbar_wait(&acc_full, 0);
-    tc_fence_after_sync();
-    G2_PHASE(2);
-    for (int task = warp; task < 4 * T; task += G2_NPW) {
-      const int t = task >> 2, sub = task & 3;
-      bool any = false;
-      for (int f = 0; f < C3P_NCELL; ++f) any |= ((active[f] >> t) & 1u) != 0;
-      const int pt = t * 128 + sub * 32 + lane;
-      int row = rowid[pt];
-      const bool poison = row < -1;
-      if (poison) row = -2 - row;
-      for (int c0_ = 0; c0_ < Nout; c0_ += 32) {
-        float v[32];
-        if (any) {
-          tmem_ld_32x32(tmem + ((uint32_t)(sub * 32) << 16) + (uint32_t)(t * Nout + c0_), v);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        if (row >= 0) {
-          float* o = a.out + (size_t)row * Nout + c0_;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (c0_ + j < Nout) {
-              float4 w4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (poison) w4 = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
-                                           __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
-              *reinterpret_cast<float4*>(o + j) = w4;
-            }
-          }
-        }
-      }
-    }
-    G2_PHASE(3);
-    if (timed)
-      for (int i = 0; i < 8; ++i) atomicAdd(&g2_phase_cycles[i], ph[i]);
-  } else if (warp == G2_NPW) {
-    // =========================== MMA issuer (one thread) ============================================
-    // Per 32-channel panel: 4 K steps of (A_hi W_hi, A_lo W_hi), then 4 K steps of A_hi W_lo, so the lo half of
-    // a weight panel is needed 512 MMA cycles after its hi half and the hi unit is released before the lo unit.
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, Nout);
-      const uint64_t a_desc0 = make_smem_desc(smem_u32(a_base)), w_desc0 = make_smem_desc(smem_u32(w_base));
-      const uint64_t a_lo_off = (uint64_t)((128 * PANEL_ROW_BYTES) >> 4);
-      const uint64_t a_step = (uint64_t)(G2_A_STAGE >> 4), w_step = (uint64_t)(unit_bytes >> 4);
-      unsigned started = 0;
-      int aslot = 0, wslot = 0;
-      uint32_t aphase = 0, wphase = 0;
-      for (int f = 0; f < C3P_NCELL; ++f) {
-        const unsigned act = active[f];
-        if (!act) continue;
-        const int t_first = __ffs(act) - 1, t_last = 31 - __clz(act);
-        for (int kb = 0; kb < a.nkb; ++kb) {
-          int us[2 * NKC];
-          uint32_t up[2 * NKC];
-#pragma unroll
-          for (int i = 0; i < 2 * NKC; ++i) {
-            us[i] = wslot; up[i] = wphase;
-            if (++wslot == NWU) { wslot = 0; wphase ^= 1u; }
-          }
-          for (int t = 0; t < T; ++t) {
-            if (!((act >> t) & 1u)) continue;
-            const uint32_t d = tmem + (uint32_t)(t * Nout);
-            uint32_t acc_flag = (started >> t) & 1u;
-            started |= 1u << t;
+            for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, 128 * PANEL_ROW_BYTES, acc[kc]);
+          } else {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int kc = 0; kc < NKC; ++kc) {
-              if (t == t_first) mbar_wait(&w_full[us[2 * kc]], up[2 * kc]);
-              mbar_wait(&a_full[aslot], aphase);
-              tc_fence_after_sync();
-              const uint64_t dah = a_desc0 + (uint64_t)aslot * a_step, dal = dah + a_lo_off;
-              const uint64_t dwh = w_desc0 + (uint64_t)us[2 * kc] * w_step;
-              const uint64_t dwl = w_desc0 + (uint64_t)us[2 * kc + 1] * w_step;
+              *reinterpret_cast<float4*>(stage[kc] + o) = z;
+              *reinterpret_cast<float4*>(stage[kc] + o + 128 * PANEL_ROW_BYTES) = z;
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          int sl = p_aslot;
 #pragma unroll
-              for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
-                const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
-                mma_tf32(d, dah + adv, dwh + adv, idesc, acc_flag);
-                mma_tf32(d, dal + adv, dwh + adv, idesc, 1u);
-                acc_flag = 1u;
-              }
-              if (t == t_last) mma_commit(&w_empty[us[2 * kc]]);
-              if (t == t_first) {
-                mbar_wait(&w_full[us[2 * kc + 1]], up[2 * kc + 1]);
-                tc_fence_after_sync();
-              }
+          for (int kc = 0; kc < NKC; ++kc) {
+            mbar_arrive(&a_full[sl]);
+            if (++sl == NAS) sl = 0;
+          }
+        }
 #pragma unroll
-              for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
-                const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
-                mma_tf32(d, dah + adv, dwl + adv, idesc, 1u);
+        for (int kc = 0; kc < NKC; ++kc)
+          if (++p_aslot == NAS) { p_aslot = 0; ++p_awrap; }
+        ++p_g;
+        c0 = n0; c1 = n1; hc = hn;
+        G2_PHASE(7);
+      }
+      ++p_g;  // the END slot
+      if (timed) { tk = clock64(); ph[1] += (unsigned)(tk - tl); }
+      // =========================== epilogue: TMEM -> registers -> global ==============================
+      mbar_wait(&acc_full, (uint32_t)(chunk & 1));
+      tc_fence_after_sync();
+      G2_PHASE(2);
+      for (int task = warp; task < 4 * T; task += G2_NPW) {
+        const int t = task >> 2, sub = task & 3;
+        bool any = false;
+        for (int f = 0; f < C3P_NCELL; ++f) any |= ((active[f] >> t) & 1u) != 0;
+        const int pt = t * 128 + sub * 32 + lane;
+        int row = rowid[pt];
+        const bool poison = row < -1;
+        if (poison) row = -2 - row;
+        for (int c0_ = 0; c0_ < Nout; c0_ += 32) {
+          float v[32];
+          if (any) {
+            tmem_ld_32x32(tmem + ((uint32_t)(sub * 32) << 16) + (uint32_t)(t * Nout + c0_), v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (row >= 0) {
+            float* o = a.out + (size_t)row * Nout + c0_;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (c0_ + j < Nout) {
+                float4 w4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (poison) w4 = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
+                                             __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+                *reinterpret_cast<float4*>(o + j) = w4;
               }
-              mma_commit(&a_empty[aslot]);
-              if (t == t_last) mma_commit(&w_empty[us[2 * kc + 1]]);
-              if (++aslot == NAS) { aslot = 0; aphase ^= 1u; }
             }
           }
         }
       }
-      mma_commit(&acc_full);
-    }
-  } else if (warp == G2_NPW + 1) {
-    // =========================== weight loader (one thread) =========================================
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t wrap = 0;
-      const int units_per_cell = a.nkb * NKC * 2;
-      for (int f = 0; f < C3P_NCELL; ++f) {
-        if (!active[f]) continue;
-        for (int u = 0; u < units_per_cell; ++u) {
-          if (wrap >= 1) mbar_wait(&w_empty[slot], (wrap - 1) & 1u);
-          mbar_arrive_expect_tx(&w_full[slot], unit_bytes);
-          bulk_copy_g2s(w_base + (size_t)slot * unit_bytes,
-                        a.wp + ((size_t)f * units_per_cell + u) * unit_bytes, unit_bytes, &w_full[slot]);
-          if (++slot == NWU) { slot = 0; ++wrap; }
+      G2_PHASE(3);
+    } else if (warp == G2_NPW) {
+      // =========================== MMA issuer (one thread) ============================================
+      // Per 32-channel panel: 4 K steps of (A_hi W_hi, A_lo W_hi), then 4 K steps of A_hi W_lo, so the lo half of
+      // a weight panel is needed 512 MMA cycles after its hi half and the hi unit is released before the lo unit.
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_tf32(128, Nout);
+        const uint64_t a_desc0 = make_smem_desc(smem_u32(a_base)), w_desc0 = make_smem_desc(smem_u32(w_base));
+        const uint64_t a_lo_off = (uint64_t)((128 * PANEL_ROW_BYTES) >> 4);
+        const uint64_t a_step = (uint64_t)(G2_A_STAGE >> 4), w_step = (uint64_t)(unit_bytes >> 4);
+        unsigned started = 0;
+        for (int f = 0; f < C3P_NCELL; ++f) {
+          const unsigned act = active[f];
+          if (!act) continue;
+          const int t_first = __ffs(act) - 1, t_last = 31 - __clz(act);
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            int us[2 * NKC];
+            uint32_t up[2 * NKC];
+#pragma unroll
+            for (int i = 0; i < 2 * NKC; ++i) {
+              us[i] = m_wslot; up[i] = m_wphase;
+              if (++m_wslot == NWU) { m_wslot = 0; m_wphase ^= 1u; }
+            }
+            for (int t = 0; t < T; ++t) {
+              if (!((act >> t) & 1u)) continue;
+              const uint32_t d = tmem + (uint32_t)(t * Nout);
+              uint32_t acc_flag = (started >> t) & 1u;
+              started |= 1u << t;
+#pragma unroll
+              for (int kc = 0; kc < NKC; ++kc) {
+                if (t == t_first) mbar_wait(&w_full[us[2 * kc]], up[2 * kc]);
+                mbar_wait(&a_full[m_aslot], m_aphase);
+                tc_fence_after_sync();
+                const uint64_t dah = a_desc0 + (uint64_t)m_aslot * a_step, dal = dah + a_lo_off;
+                const uint64_t dwh = w_desc0 + (uint64_t)us[2 * kc] * w_step;
+                const uint64_t dwl = w_desc0 + (uint64_t)us[2 * kc + 1] * w_step;
+#pragma unroll
+                for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
+                  const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                  mma_tf32(d, dah + adv, dwh + adv, idesc, acc_flag);
+                  mma_tf32(d, dal + adv, dwh + adv, idesc, 1u);
+                  acc_flag = 1u;
+                }
+                if (t == t_last) mma_commit(&w_empty[us[2 * kc]]);
+                if (t == t_first) {
+                  mbar_wait(&w_full[us[2 * kc + 1]], up[2 * kc + 1]);
+                  tc_fence_after_sync();
+                }
+#pragma unroll
+                for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
+                  const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                  mma_tf32(d, dah + adv, dwl + adv, idesc, 1u);
+                }
+                mma_commit(&a_empty[m_aslot]);
+                if (t == t_last) mma_commit(&w_empty[us[2 * kc + 1]]);
+                if (++m_aslot == NAS) { m_aslot = 0; m_aphase ^= 1u; }
+              }
+            }
+          }
         }
+        mma_commit(&acc_full);
       }
-    }
-  } else {
-    // =========================== item-list loader (one thread) ======================================
-    if (lane == 0) {
-      int g = 0;
-      for (int f = 0; f < C3P_NCELL; ++f) {
-        const unsigned act = active[f];
-        if (!act) continue;
-        for (int kb = 0; kb < a.nkb; ++kb) {
-          for (int t = 0; t < T; ++t) {
-            if (!((act >> t) & 1u)) continue;
-            const int slot = g & (G2_NIS - 1), use = g / G2_NIS;
-            if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
-            hdr[slot] = kb;
-            mbar_arrive_expect_tx(&it_full[slot], 128 * sizeof(uint2));
-            bulk_copy_g2s(items + slot * 128, a.g_items + ((sub0 + t) * C3P_NCELL + f) * 128, 128 * sizeof(uint2),
-                          &it_full[slot]);
-            ++g;
+    } else if (warp == G2_NPW + 1) {
+      // =========================== weight loader (one thread) =========================================
+      if (lane == 0) {
+        const int units_per_cell = a.nkb * NKC * 2;
+        for (int f = 0; f < C3P_NCELL; ++f) {
+          if (!active[f]) continue;
+          for (int u = 0; u < units_per_cell; ++u) {
+            if (l_wrap >= 1) mbar_wait(&w_empty[l_slot], (l_wrap - 1) & 1u);
+            mbar_arrive_expect_tx(&w_full[l_slot], unit_bytes);
+            bulk_copy_g2s(w_base + (size_t)l_slot * unit_bytes,
+                          a.wp + ((size_t)f * units_per_cell + u) * unit_bytes, unit_bytes, &w_full[l_slot]);
+            if (++l_slot == NWU) { l_slot = 0; ++l_wrap; }
           }
         }
       }
-      const int slot = g & (G2_NIS - 1), use = g / G2_NIS;
-      if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
-      hdr[slot] = G2_END;
-      mbar_arrive(&it_full[slot]);
+    } else {
+      // =========================== item-list loader (one thread) ======================================
+      if (lane == 0) {
+        auto acquire = [&]() -> int {
+          const int slot = i_g & (G2_NIS - 1), use = i_g / G2_NIS;
+          if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
+          ++i_g;
+          return slot;
+        };
+        for (int f = 0; f < C3P_NCELL; ++f) {
+          const unsigned act = active[f];
+          if (!act) continue;
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            for (int t = 0; t < T; ++t) {
+              if (!((act >> t) & 1u)) continue;
+              const int slot = acquire();
+              hdr[slot] = kb;
+              mbar_arrive_expect_tx(&it_full[slot], 128 * sizeof(uint2));
+              bulk_copy_g2s(items + slot * 128, a.g_items + ((sub0 + t) * C3P_NCELL + f) * 128,
+                            128 * sizeof(uint2), &it_full[slot]);
+            }
+          }
+        }
+        const int slot = acquire();
+        hdr[slot] = G2_END;
+        mbar_arrive(&it_full[slot]);
+      }
     }
+    // the next chunk overwrites the row table, the group masks and (through the MMAs) the accumulators
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
   }
-  tc_fence_before_sync();
-  __syncthreads();
+  if (timed)
+    for (int i = 0; i < 8; ++i) atomicAdd(&g2_phase_cycles[i], (unsigned long long)ph[i]);
   if (warp == G2_NPW + 1) tmem_dealloc(tmem, 512);
 }
 
@@ -440,24 +484,13 @@ struct G2Config {
 };
 
 // Csrc = contraction width per cell (Cin forward, Cout backward), Nout = output width.
-static bool g2_config(int N, long long capacity, int Csrc, int Nout, G2Config* c, long long points = 0) {
+static bool g2_config(int N, long long capacity, int Csrc, int Nout, G2Config* c) {
   if (N > 65535) return false;                // members per cell are packed in 24 bits, rows in 8
   if (capacity >= (1LL << 32)) return false;  // list positions are 32-bit
   if (Csrc % 32 || Nout % 16 || Csrc < 32 || Nout < 16 || Nout > 256) return false;
   c->NKC = (Csrc % 64 == 0) ? 2 : 1;
   c->nkb = Csrc / (32 * c->NKC);
   c->T = 512 / Nout >= 4 ? 4 : (512 / Nout);
-  // Wave quantisation (one CTA per SM): a smaller T can need fewer sub-tile rounds in total.
-  if (points > 0 && c->T == 4) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    (void)cudaGetLastError();
-    auto rounds = [&](int T) {
-      const long long tiles = (points + (long long)T * 128 - 1) / ((long long)T * 128);
-      return ((tiles + sms - 1) / sms) * T;
-    };
-    if (rounds(3) < rounds(4)) c->T = 3;
-  }
   const size_t budget = 227 * 1024 - 2048;  // static shared memory (barriers, masks) + alignment slack
   const size_t unit = (size_t)Nout * PANEL_ROW_BYTES;
   const size_t tables = (size_t)c->T * 128 * 4 + (size_t)G2_NIS * 128 * 8;
@@ -485,7 +518,7 @@ size_t group_items_bytes(long long pts, int rows) {
   const long long subtiles = (pts + rows - 1) / rows;
   return align_up((size_t)subtiles * C3P_NCELL * rows * sizeof(uint2)) +
          align_up((size_t)subtiles * C3P_NCELL * sizeof(int)) + align_up((size_t)subtiles * rows * sizeof(int)) +
-         align_up((size_t)subtiles * sizeof(unsigned));
+         align_up((size_t)subtiles * sizeof(unsigned)) + 256;
 }
 
 GroupItems carve_group_items(void* scratch, long long pts, int rows) {
@@ -496,7 +529,8 @@ GroupItems carve_group_items(void* scratch, long long pts, int rows) {
   gi.items = reinterpret_cast<uint2*>(sp); sp += align_up((size_t)subtiles * C3P_NCELL * rows * sizeof(uint2));
   gi.nnz = reinterpret_cast<int*>(sp); sp += align_up((size_t)subtiles * C3P_NCELL * sizeof(int));
   gi.rowid = reinterpret_cast<int*>(sp); sp += align_up((size_t)subtiles * rows * sizeof(int));
-  gi.mask = reinterpret_cast<unsigned*>(sp);
+  gi.mask = reinterpret_cast<unsigned*>(sp); sp += align_up((size_t)subtiles * sizeof(unsigned));
+  gi.counter = reinterpret_cast<unsigned*>(sp);
   return gi;
 }
 
@@ -510,11 +544,11 @@ int launch_group_items(const conv3p_geom_t* g, const PlanView& v, bool backward_
     if (rows == 128)
       k_group_items<128><<<(unsigned)gi.subtiles, 128, 0, stream>>>(cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts,
                                                                     g->pair_capacity, g->N, gi.items, gi.nnz,
-                                                                    gi.rowid, gi.mask);
+                                                                    gi.rowid, gi.mask, gi.counter);
     else
       k_group_items<64><<<(unsigned)gi.subtiles, 64, 0, stream>>>(cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts,
                                                                   g->pair_capacity, g->N, gi.items, gi.nnz, gi.rowid,
-                                                                  gi.mask);
+                                                                  gi.mask, gi.counter);
   }
   C3P_LAUNCH_CHECK("k_group_items");
   return CONV3P_OK;
@@ -527,7 +561,7 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
                        cudaStream_t stream) {
   G2Config c;
   const long long pts = (long long)g->B * g->N;
-  if (!g2_config(g->N, g->pair_capacity, Csrc, Nout, &c, pts)) return CONV3P_ERR_UNSUPPORTED;
+  if (!g2_config(g->N, g->pair_capacity, Csrc, Nout, &c)) return CONV3P_ERR_UNSUPPORTED;
   if (pts == 0) return CONV3P_OK;
   if (!scratch || scratch_bytes < gather_mma2_scratch_bytes(g)) return CONV3P_ERR_BUFFER_TOO_SMALL;
   const GroupItems gi = carve_group_items(scratch, pts, 128);
@@ -540,12 +574,15 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
   a.src = src; a.wp = static_cast<const unsigned char*>(wp); a.out = out;
   a.rows = weighted ? v.bwd_row : v.pair_row;
   a.weights = weighted ? v.bwd_weight : nullptr;
-  a.g_items = gi.items; a.g_nnz = gi.nnz; a.g_rowid = gi.rowid;
+  a.g_items = gi.items; a.g_nnz = gi.nnz; a.g_rowid = gi.rowid; a.counter = gi.counter;
   a.total_points = pts; a.subtiles = subtiles;
   a.N = g->N; a.Csrc = Csrc; a.Nout = Nout;
   a.nkb = c.nkb; a.T = c.T; a.NAS = c.NAS; a.NWU = c.NWU;
   a.debug = engine() >= 64 ? (engine() & ~(64 | 128)) : 0;
-  const long long tiles = (subtiles + c.T - 1) / c.T;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  (void)cudaGetLastError();
+  const long long tiles = subtiles < sms ? subtiles : sms;  // persistent CTAs, one per SM
   auto launch = [&](auto kern) -> int {
     C3P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     {

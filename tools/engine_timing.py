@@ -31,7 +31,7 @@ for label, fn in [("forward", lambda: conv3p_forward(plan, pr["input"], pr["filt
     fn(); torch.cuda.synchronize()
     L.conv3p_debug_phase_cycles(buf)
     L.conv3p_set_engine(0)
-    tiles = (B * N + 383) // 384
+    tiles = min(148, (B * N + 127) // 128)
     v = [x / tiles for x in buf]
     print(f"{label}: k_gather_mma2 cycles per CTA (thread 0): prologue {v[0]:.0f} | producer loop {v[1]:.0f} | "
           f"wait last MMA {v[2]:.0f} | epilogue {v[3]:.0f} || in loop: item fetch {v[4]:.0f} | gather 0 {v[5]:.0f} | "
