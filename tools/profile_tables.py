@@ -1,5 +1,5 @@
 """Turns the round's raw artefacts in gpurun_out/ into the tables committed under profiles/.
-usage: python tools/profile_tables.py  (after the gpurun collection call in profiles/r1_summary.md)"""
+usage: python tools/profile_tables.py [tag]  (after `gpurun -- bash tools/collect.sh <tag>`; tag defaults to r1)"""
 import csv
 import json
 import os
@@ -9,8 +9,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
 NAMES = {"k_gather_mma_tc<2, 0>": "k_forward_tc", "k_gather_mma_tc<2, 1>": "k_backward_input_tc",
-         "k_gather_mma_tc<1, 0>": "k_forward_tc", "k_gather_mma_tc<1, 1>": "k_backward_input_tc"}
+         "k_gather_mma_tc<1, 0>": "k_forward_tc", "k_gather_mma_tc<1, 1>": "k_backward_input_tc",
+         "k_gather_mma2<2, 0>": "k_forward_tc", "k_gather_mma2<2, 1>": "k_backward_input_tc",
+         "k_gather_mma2<1, 0>": "k_forward_tc", "k_gather_mma2<1, 1>": "k_backward_input_tc",
+         "k_backward_filter2": "k_backward_filter_tc", "k_backward_fused": "k_backward_fused"}
 
 
 def ncu_raw(rep):
@@ -20,7 +24,7 @@ def ncu_raw(rep):
 
 
 def main():
-    hdr, units, rows = ncu_raw(os.path.join(G, "prof_r1_final.ncu-rep"))
+    hdr, units, rows = ncu_raw(os.path.join(G, f"prof_{TAG}.ncu-rep"))
     g = lambda r, k: r[hdr.index(k)]
     conv = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
     traffic, lines = {}, []
@@ -35,6 +39,8 @@ def main():
                 key = b
         rd = float(g(r, "dram__bytes_read.sum").replace(",", "")) * conv[units[hdr.index("dram__bytes_read.sum")]]
         wr = float(g(r, "dram__bytes_write.sum").replace(",", "")) * conv[units[hdr.index("dram__bytes_write.sum")]]
+        if key in traffic:   # several launches of one kernel (k_group_items): keep the first
+            key = key + "#" + str(sum(1 for k in traffic if k.startswith(key)))
         traffic[key] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
                         "time_ms": float(g(r, "gpu__time_duration.sum"))}
         lines.append(f"| `{key}` | {float(g(r, 'gpu__time_duration.sum')):.3f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | "
@@ -46,18 +52,19 @@ def main():
                      f"{g(r, 'launch__registers_per_thread')} |")
     json.dump({"headline": traffic}, open(os.path.join(P, "kernel_traffic.json"), "w"), indent=1)
     print("\n".join(lines))
-    for src, dst in [("bench_r1.json", "r1_bench_headline.json"), ("bench_r1_reference.json", "r1_bench_reference_arm.json"),
-                     ("launches_r1.csv", "r1_launches_headline.csv"), ("bench_r1_s3dis_l1.json", "r1_bench_s3dis_l1.json"),
-                     ("bench_r1_s3dis_l5.json", "r1_bench_s3dis_l5.json"), ("bench_r1_modelnet_l2.json", "r1_bench_modelnet_l2.json")]:
+    for src, dst in [(f"bench_{TAG}.json", "r1_bench_headline.json"), (f"bench_{TAG}_reference.json", "r1_bench_reference_arm.json"),
+                     (f"launches_{TAG}.csv", "r1_launches_headline.csv"), (f"bench_{TAG}_s3dis_l1.json", "r1_bench_s3dis_l1.json"),
+                     (f"bench_{TAG}_s3dis_l5.json", "r1_bench_s3dis_l5.json"), (f"bench_{TAG}_modelnet_l2.json", "r1_bench_modelnet_l2.json"),
+                     (f"engine_timing_{TAG}.txt", "r1_engine_timing.txt")]:
         if os.path.exists(os.path.join(G, src)):
             open(os.path.join(P, dst), "w").write(open(os.path.join(G, src)).read())
-    d = json.load(open(os.path.join(G, "bench_r1.json")))
+    d = json.load(open(os.path.join(G, f"bench_{TAG}.json")))
     print("\nheadline:", d["value"], "points/s", d["ms_per_step"], "ms/step; e2e", d["e2e"]["value"], "; cpu", d["cpu_baseline"]["value"])
     print("roofline:", {k: d["roofline"][k] for k in ("kernel", "achieved", "frac")})
     for k, v in d["kernels"].items():
         print("  ", k, v)
     for w in ("s3dis_l1", "s3dis_l5", "modelnet_l2"):
-        f = os.path.join(G, f"bench_r1_{w}.json")
+        f = os.path.join(G, f"bench_{TAG}_{w}.json")
         if os.path.exists(f):
             x = json.load(open(f))
             print(w, x["value"], x["ms_per_step"], "cpu", x.get("cpu_baseline", {}).get("value"))
