@@ -297,7 +297,7 @@ def gpu_arm(args):
 
     # e2e (host buffers): every step copies its pinned-host inputs to the device, rebuilds the plan, runs
     # forward + backward (+ the all-reduce) and copies output / grad_input / grad_filter back to pinned host
-    # memory; copies of neighbouring steps overlap the kernels (three streams, double-buffered staging).
+    # memory; copies of neighbouring steps overlap the kernels (three streams, three staging slots).
     from pointwise_b200.host_api import HostConv3p
     pipe = HostConv3p(hi - lo, N, Cin, Cout, stride, VOXEL, device=device, capacity=capacity)
     ar = allreduce_grad_filter if world > 1 else None
@@ -306,9 +306,10 @@ def gpu_arm(args):
         tickets = []
         for _ in range(steps):
             tickets.append(pipe.submit(host["points"], host["input"], host["filter"], host["grad_out"], ar))
-            if len(tickets) >= 2:
-                pipe.fetch(tickets[-2])
-        pipe.fetch(tickets[-1])
+            if len(tickets) >= pipe.depth:
+                pipe.fetch(tickets[-pipe.depth])
+        for t in tickets[-(pipe.depth - 1):]:
+            pipe.fetch(t)
 
     run_e2e(3)
     e2e_steps = max(4, args.steps)

@@ -109,6 +109,11 @@ int conv3p_plan_stats(const conv3p_geom_t* geom, const void* plan, conv3p_plan_s
 /* ---- the operator on a built plan ------------------------------------------------------------- */
 
 size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout);
+/* >= conv3p_scratch_bytes.  A backward call given this much scratch lets the grad_input kernel leave its
+ * per-(point, cell) aggregates of grad_output in the scratch tail (27*Cout floats per point) for the grad_filter
+ * kernel, which then does not walk the backward lists a second time; with only conv3p_scratch_bytes the result
+ * is the same, the weight gradient just gathers on its own. */
+size_t conv3p_backward_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout);
 
 /* output[B,N,Cout] = Conv3p(points, input, filter); follows tf_conv3p_atrous.cpp:456-504. */
 int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float* input,

@@ -120,6 +120,17 @@ int make_view(const conv3p_geom_t* g, const void* plan, size_t plan_bytes, PlanV
   return CONV3P_OK;
 }
 
+// G store shared by the grad_input and grad_filter kernels of one backward call (gather_mma2.cu / backward_filter2.cu):
+// one Cout-wide row per (sorted position, cell), last region of the scratch buffer; 0 when the pair of kernels that
+// uses it does not apply to the shape.
+static size_t g_store_bytes(const conv3p_geom_t* g, int Cin, int Cout) {
+  if (!gather_mma2_supported(g->N, g->pair_capacity, Cout, Cin) ||
+      !backward_filter2_supported(g->N, g->pair_capacity, Cin, Cout))
+    return 0;
+  const size_t pts = ((size_t)g->B * g->N + 127) / 128 * 128;
+  return align_up(pts * C3P_NCELL * (size_t)Cout * sizeof(float));
+}
+
 static int check_channels(int Cin, int Cout) {
   if (Cin < 1 || Cout < 1 || Cin > (1 << 16) || Cout > (1 << 16)) return CONV3P_ERR_INVALID_ARGUMENT;
   return CONV3P_OK;
@@ -271,7 +282,13 @@ size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
     const size_t t = backward_filter2_scratch_bytes(geom, Cin, Cout);
     if (t > filt) filt = t;
   }
-  return weight_panel_bytes(Cin, Cout) + tc_items_bytes(geom, Cin, Cout) + filt + 256;
+  return weight_panel_bytes(Cin, Cout) + tc_items_bytes(geom, Cin, Cout) + align_up(filt) + 256;
+}
+
+size_t conv3p_backward_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
+  const size_t base = conv3p_scratch_bytes(geom, Cin, Cout);
+  if (!base) return 0;
+  return base + g_store_bytes(geom, Cin, Cout);
 }
 
 int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
@@ -303,12 +320,22 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
   st = make_view(geom, plan, conv3p_plan_bytes(geom), &v);
   if (st) return st;
   if (!grad_output && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
+  // both gradients on the tensor-core kernels: the grad_input kernel leaves its aggregated rows in the G store
+  // (tail of the scratch buffer) for the grad_filter kernel; engine bit 256 switches the sharing off (A/B timing)
+  float* g_store = nullptr;
+  {
+    const size_t gsb = g_store_bytes(geom, Cin, Cout);
+    const size_t base = conv3p_scratch_bytes(geom, Cin, Cout);
+    if (grad_input && grad_filter && gsb && scratch && scratch_bytes >= base + gsb && engine() != 1 &&
+        !(engine() & (128 | 256)))
+      g_store = reinterpret_cast<float*>(static_cast<char*>(scratch) + base);
+  }
   if (grad_input) {
     if (!filter) return CONV3P_ERR_INVALID_ARGUMENT;
     if (engine() != 1 && backward_input_tc_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
       if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
       st = launch_backward_input_tc(geom, v, grad_output, filter, Cin, Cout, grad_input, scratch,
-                                    scratch_bytes, stream);
+                                    scratch_bytes, stream, g_store);
     } else if (engine() != 3 && small_channels_supported(Cin, Cout)) {
       st = launch_backward_input_small(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);
     } else {
@@ -322,7 +349,7 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
     if (!scratch || scratch_bytes < wpb) return CONV3P_ERR_BUFFER_TOO_SMALL;
     if (engine() != 1 && !(engine() & 128) && backward_filter2_supported(geom->N, geom->pair_capacity, Cin, Cout))
       st = launch_backward_filter2(geom, v, grad_output, input, Cin, Cout, grad_filter,
-                                   static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);
+                                   static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream, g_store);
     else if (engine() != 1 && backward_filter_tc_supported(geom->N, geom->pair_capacity, Cin, Cout))
       st = launch_backward_filter_tc(geom, v, grad_output, input, Cin, Cout, grad_filter,
                                      static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);

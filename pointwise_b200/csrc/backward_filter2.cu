@@ -11,7 +11,11 @@
 //    global loads each;
 //  * a quarter-warp gathers ALL 128 channels of its row (four 32-channel panels, two members per round), so
 //    list ids, weights and predicates are paid once per 512-byte row rather than once per 256 bytes, and the
-//    accumulation is packed FFMA2 with weight-0 padding instead of zero-selects.
+//    accumulation is packed FFMA2 with weight-0 padding instead of zero-selects;
+//  * when grad_input is computed in the same call by k_gather_mma2, that kernel has already aggregated exactly these
+//    G_f rows and left them in the G store ([sorted position][27][Cout], only non-empty (point, cell) slots are
+//    written): the producers then read ONE 512-byte row per non-empty item (prefetched one group ahead) instead of
+//    walking its list -- 4.2x fewer row reads on the bench cloud and no ids or weights (template FROM_STORE).
 //
 // Warp roles: warps [0, 16) producers (also the flush), 16 = MMA issuer + TMEM allocator, 17 = item-list loader.
 #include "common.cuh"
@@ -39,10 +43,12 @@ struct W2Args {
   const int* g_rowid;      // [tiles*64]
   const unsigned* g_mask;  // [tiles] bit f: some point of the tile has members in cell f
   float* partial;          // [gridDim.x][27*Cin*Cout]
+  const float* g_store;    // FROM_STORE: G_f rows [tiles*64][27][Cout] written by k_gather_mma2
   long long total_points, tiles;
   int Cin, Cout, FG;       // FG = accumulators (cells) per pass
 };
 
+template <bool FROM_STORE>
 __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Cin = a.Cin, Cout = a.Cout, FG = a.FG;
@@ -101,12 +107,38 @@ __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args
       if (lane == 0) mbar_arrive(&it_empty[slot]);
       it.pos = u.x; it.p = (int)(u.y & 255u); it.n = h != W2_END ? (int)(u.y >> 8) : 0;
       it.inv = 0.f; it.w = 0.f;
-      g2_prefetch<true>(it, a.rows, a.weights, 0, l8, max_row);
+      if (!FROM_STORE) g2_prefetch<true>(it, a.rows, a.weights, 0, l8, max_row);
       return h;
     };
+    // FROM_STORE: the item's aggregated row (hdr = tile-local index << 8 | cell)
+    auto fetch_row = [&](const G2Item& it, int h, float4 (&v)[W2_GP]) {
+      const float* src = a.g_store + (((size_t)(tile_lo + (h >> 8)) * W2_PTS + it.p) * C3P_NCELL + (h & 255)) * Cout +
+                         l8 * 4;
+#pragma unroll
+      for (int kc = 0; kc < W2_GP; ++kc)
+        v[kc] = it.n > 0 ? ldg4(src + kc * PANEL_K) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
     int visit = 0, g = 0;
-    G2Item cur;
-    read_item(0, cur);
+    // Look-ahead queue of work items: the next item, with its first list ids (gather mode) or its G row (store mode)
+    // in flight.  (Three rows of look-ahead were measured slower: the kernel is bound by shared-memory bandwidth --
+    // operand reads of the MMAs plus the panel stores -- not by the latency of the row loads, and the extra registers
+    // spill.)
+    constexpr int LOOK = 1;
+    G2Item ahead[LOOK];
+    float4 ahead_row[LOOK][W2_GP];
+    int n_read = 0;
+    bool ended = false;
+    auto pull = [&](G2Item& it, float4 (&r)[W2_GP]) {
+      if (ended) {                 // nothing is published after the END marker
+        it.n = 0; it.p = 0; it.pos = 0u;
+        return;
+      }
+      const int h = read_item(n_read++, it);
+      ended = h == W2_END;
+      if (FROM_STORE) fetch_row(it, ended ? 0 : h, r);
+    };
+#pragma unroll
+    for (int d = 0; d < LOOK; ++d) pull(ahead[d], ahead_row[d]);
     for (int pass = 0; pass < npass; ++pass) {
       const int f0 = pass * FG, f1 = min(C3P_NCELL, f0 + FG);
       const unsigned pass_bits = ((f1 - f0) == 32 ? ~0u : ((1u << (f1 - f0)) - 1u)) << f0;
@@ -139,12 +171,22 @@ __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args
         }
         // ---- one G stage per active cell -----------------------------------------------------------------
         for (unsigned todo = mask; todo; todo &= todo - 1) {
-          G2Item nxt;
-          read_item(g + 1, nxt);
-          int nmax = max(cur.n, __shfl_xor_sync(C3P_FULL_MASK, cur.n, 8));
-          nmax = max(nmax, __shfl_xor_sync(C3P_FULL_MASK, nmax, 16));
+          G2Item cur = ahead[0];
           float4 acc[W2_GP];
-          g2_gather<W2_GP, 2, true>(acc, cur, nmax, a.grad_out, Cout, 0, a.rows, a.weights, l8, max_row);
+#pragma unroll
+          for (int kc = 0; kc < W2_GP; ++kc) acc[kc] = ahead_row[0][kc];
+#pragma unroll
+          for (int d = 0; d + 1 < LOOK; ++d) {
+            ahead[d] = ahead[d + 1];
+#pragma unroll
+            for (int kc = 0; kc < W2_GP; ++kc) ahead_row[d][kc] = ahead_row[d + 1][kc];
+          }
+          pull(ahead[LOOK - 1], ahead_row[LOOK - 1]);
+          if (!FROM_STORE) {
+            int nmax = max(cur.n, __shfl_xor_sync(C3P_FULL_MASK, cur.n, 8));
+            nmax = max(nmax, __shfl_xor_sync(C3P_FULL_MASK, nmax, 16));
+            g2_gather<W2_GP, 2, true>(acc, cur, nmax, a.grad_out, Cout, 0, a.rows, a.weights, l8, max_row);
+          }
           const int slot = g & 1, use = g >> 1;
           if (use >= 1) mbar_wait(&g_empty[slot], (uint32_t)((use - 1) & 1));
           unsigned char* stage = g_base + (size_t)slot * 2 * g_half + panel_chunk_offset_mn(cur.p, l8);
@@ -154,7 +196,6 @@ __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args
           __syncwarp();
           if (lane == 0) mbar_arrive(&g_full[slot]);
           ++g;
-          cur = nxt;
         }
         ++visit;
       }
@@ -245,7 +286,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args
             const int f = __ffs(todo) - 1;
             const int slot = g & (W2_NIS - 1), use = g / W2_NIS;
             if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
-            hdr[slot] = f;
+            hdr[slot] = f | ((int)(tile - tile_lo) << 8);
             mbar_arrive_expect_tx(&it_full[slot], W2_PTS * sizeof(uint2));
             bulk_copy_g2s(items + slot * W2_PTS, a.g_items + (tile * C3P_NCELL + f) * W2_PTS,
                           W2_PTS * sizeof(uint2), &it_full[slot]);
@@ -302,7 +343,7 @@ size_t backward_filter2_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout)
 
 int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const float* grad_out, const float* input,
                             int Cin, int Cout, float* grad_filter, void* scratch, size_t scratch_bytes,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const float* g_store) {
   const long long nW = (long long)C3P_NCELL * Cin * Cout;
   const long long pts = (long long)g->B * g->N;
   if (pts == 0) {
@@ -318,14 +359,18 @@ int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const flo
   if (grid > 256) return CONV3P_ERR_UNSUPPORTED;
   W2Args a{};
   a.grad_out = grad_out; a.input = input; a.rows = v.bwd_row; a.weights = v.bwd_weight;
-  a.g_items = gi.items; a.g_rowid = gi.rowid; a.g_mask = gi.mask; a.partial = partial;
+  a.g_items = gi.items; a.g_rowid = gi.rowid; a.g_mask = gi.mask; a.partial = partial; a.g_store = g_store;
   a.total_points = pts; a.tiles = gi.subtiles; a.Cin = Cin; a.Cout = Cout;
   a.FG = 512 / Cin > 8 ? 8 : 512 / Cin;
   const size_t smem = w2_smem_bytes(Cin);
-  C3P_CUDA(cudaFuncSetAttribute(k_backward_filter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
+  if (g_store) {
+    C3P_CUDA(cudaFuncSetAttribute(k_backward_filter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchTimer timer_("k_backward_filter_tc", stream);
-    k_backward_filter2<<<grid, W2_THREADS, smem, stream>>>(a);
+    k_backward_filter2<true><<<grid, W2_THREADS, smem, stream>>>(a);
+  } else {
+    C3P_CUDA(cudaFuncSetAttribute(k_backward_filter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LaunchTimer timer_("k_backward_filter_tc", stream);
+    k_backward_filter2<false><<<grid, W2_THREADS, smem, stream>>>(a);
   }
   C3P_LAUNCH_CHECK("k_backward_filter_tc");
   {

@@ -68,7 +68,7 @@ bool forward_tc_supported(int N, long long capacity, int Cin, int Cout);
 bool backward_input_tc_supported(int N, long long capacity, int Cin, int Cout);
 int launch_backward_input_tc(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
                              const float* filter, int Cin, int Cout, float* grad_input, void* scratch,
-                             size_t scratch_bytes, cudaStream_t stream);
+                             size_t scratch_bytes, cudaStream_t stream, float* g_store = nullptr);
 size_t weight_panel_bytes(int Cin, int Cout);
 int launch_prep_weight_panels(const float* filter, void* wp, int Cin, int Cout, int transposed_out,
                               cudaStream_t stream);
@@ -95,7 +95,7 @@ int launch_group_items(const conv3p_geom_t* g, const PlanView& v, bool backward_
                        const GroupItems& gi, cudaStream_t stream);
 int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* src, const void* wp, int Csrc,
                        int Nout, float* out, bool weighted, void* scratch, size_t scratch_bytes, const char* name,
-                       cudaStream_t stream);
+                       cudaStream_t stream, float* g_store = nullptr);
 // scratch layout of one forward / backward call: [weight panel images | work-item lists | grad_filter partials]
 size_t tc_items_bytes(const conv3p_geom_t* g, int Cin, int Cout);
 
@@ -110,7 +110,7 @@ bool backward_filter2_supported(int N, long long capacity, int Cin, int Cout);
 size_t backward_filter2_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout);
 int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const float* grad_out, const float* input,
                             int Cin, int Cout, float* grad_filter, void* scratch, size_t scratch_bytes,
-                            cudaStream_t stream);
+                            cudaStream_t stream, const float* g_store = nullptr);
 
 // warp-per-point fp32 engine for the reference models' small channel counts (3, 9, 13, 36)
 bool small_channels_supported(int Cin, int Cout);

@@ -458,7 +458,7 @@ int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* in
 
 int launch_backward_input_tc(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
                              const float* filter, int Cin, int Cout, float* grad_input, void* scratch,
-                             size_t scratch_bytes, cudaStream_t stream) {
+                             size_t scratch_bytes, cudaStream_t stream, float* g_store) {
   FTConfig c;
   if (!ft_config(g->N, g->pair_capacity, Cout, Cin, &c, (long long)g->B * g->N)) return CONV3P_ERR_UNSUPPORTED;
   if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
@@ -467,7 +467,8 @@ int launch_backward_input_tc(const conv3p_geom_t* g, const PlanView& v, const fl
   if (!(engine() & 128) && gather_mma2_supported(g->N, g->pair_capacity, Cout, Cin)) {
     const size_t wpb = weight_panel_bytes(Cin, Cout);
     return launch_gather_mma2(g, v, grad_out, scratch, Cout, Cin, grad_input, true,
-                              static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, "k_backward_input_tc", stream);
+                              static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, "k_backward_input_tc", stream,
+                              g_store);
   }
   FTArgs a{};
   a.src = grad_out; a.wp = static_cast<const unsigned char*>(scratch); a.out = grad_input;

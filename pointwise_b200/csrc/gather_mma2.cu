@@ -51,6 +51,10 @@ struct G2Args {
   long long total_points, subtiles;
   int N, Csrc, Nout, nkb, T, NAS, NWU;
   int debug;  // bit 32: accumulate the phase timers below
+  // WEIGHTED only, optional: the aggregated rows G_f[j, :] of every non-empty (point, cell) are also written to
+  // g_store[(sorted position * 27 + f) * Csrc ...], where the weight-gradient kernel picks them up instead of
+  // gathering the same lists a second time (backward_filter2.cu).
+  float* g_store;
 };
 
 // cycles summed over CTAs (warp 0, lane 0): prologue | producer loop | wait for the last MMA | epilogue |
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
       it_full[G2_NIS], it_empty[G2_NIS], acc_full;
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned active[C3P_NCELL];  // bit t: sub-tile t of the chunk has members in cell f
-  __shared__ int hdr[G2_NIS];             // K batch of the group in the slot, or G2_END
+  __shared__ int hdr[G2_NIS];             // group in the slot: K batch | sub-tile << 8 | cell << 16, or G2_END
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool timed = (a.debug & 32) && tid == 0;
@@ -271,9 +275,19 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
         G2Item n0, n1;
         const int hn = read_items(p_g + 1, n0, n1);
         G2_PHASE(4);
-        const int col = hc * NKC * PANEL_K;
+        const int col = (hc & 255) * NKC * PANEL_K;
         float4 acc[NKC];
         g2_gather<NKC, 4, WEIGHTED>(acc, c0, warp_max(c0.n), a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
+        // row of G_f in the store: sorted position * 27 + cell
+        float* gs = nullptr;
+        if (WEIGHTED && a.g_store)
+          gs = a.g_store + (((size_t)(sub0 + ((hc >> 8) & 255)) * 128) * C3P_NCELL + (size_t)(hc >> 16)) * a.Csrc +
+               col + l8 * 4;
+        if (WEIGHTED && gs && c0.n > 0) {
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc)
+            *reinterpret_cast<float4*>(gs + (size_t)c0.p * C3P_NCELL * a.Csrc + kc * PANEL_K) = acc[kc];
+        }
         G2_PHASE(5);
         // the ring stages of this group must have been drained by the tensor core
         unsigned char* stage[NKC];
@@ -294,8 +308,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
           for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, 128 * PANEL_ROW_BYTES, acc[kc]);
         }
         const int nmax1 = warp_max(c1.n);
-        if (nmax1 > 0)
+        if (nmax1 > 0) {
           g2_gather<NKC, 4, WEIGHTED>(acc, c1, nmax1, a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
+          if (WEIGHTED && gs && c1.n > 0) {
+#pragma unroll
+            for (int kc = 0; kc < NKC; ++kc)
+              *reinterpret_cast<float4*>(gs + (size_t)c1.p * C3P_NCELL * a.Csrc + kc * PANEL_K) = acc[kc];
+          }
+        }
         {
           const uint32_t o = panel_chunk_offset(c1.p, l8);
           if (nmax1 > 0) {
@@ -456,7 +476,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
             for (int t = 0; t < T; ++t) {
               if (!((act >> t) & 1u)) continue;
               const int slot = acquire();
-              hdr[slot] = kb;
+              hdr[slot] = kb | (t << 8) | (f << 16);
               mbar_arrive_expect_tx(&it_full[slot], 128 * sizeof(uint2));
               bulk_copy_g2s(items + slot * 128, a.g_items + ((sub0 + t) * C3P_NCELL + f) * 128,
                             128 * sizeof(uint2), &it_full[slot]);
@@ -558,7 +578,7 @@ size_t gather_mma2_scratch_bytes(const conv3p_geom_t* g) { return group_items_by
 
 int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* src, const void* wp, int Csrc,
                        int Nout, float* out, bool weighted, void* scratch, size_t scratch_bytes, const char* name,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, float* g_store) {
   G2Config c;
   const long long pts = (long long)g->B * g->N;
   if (!g2_config(g->N, g->pair_capacity, Csrc, Nout, &c)) return CONV3P_ERR_UNSUPPORTED;
@@ -578,7 +598,8 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
   a.total_points = pts; a.subtiles = subtiles;
   a.N = g->N; a.Csrc = Csrc; a.Nout = Nout;
   a.nkb = c.nkb; a.T = c.T; a.NAS = c.NAS; a.NWU = c.NWU;
-  a.debug = engine() >= 64 ? (engine() & ~(64 | 128)) : 0;
+  a.debug = engine() >= 64 ? (engine() & ~(64 | 128 | 256)) : 0;
+  a.g_store = weighted ? g_store : nullptr;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   (void)cudaGetLastError();

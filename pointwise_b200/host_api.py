@@ -3,9 +3,11 @@
 The reference is driven with numpy batches through ``session.run`` (train_modelnet40_acsd.py:123-156): every
 step feeds host arrays and fetches host results.  ``HostConv3p`` offers that shape for Conv3p forward +
 Conv3pGrad: ``submit()`` takes pinned host tensors, ``fetch()`` returns pinned host results.  Copies and compute
-run on three CUDA streams with double-buffered device staging, so the host->device copy of step k+1 and the
-device->host copy of step k-1 overlap the kernels of step k; nothing is cached between steps -- every step
-copies its own inputs, rebuilds its neighbour plan and copies its own outputs.
+run on three CUDA streams with `depth` (default 3) device staging slots, so the host->device copy of step k+1 and
+the device->host copy of step k-1 overlap the kernels of step k (with only two slots the upload of step k+1 would
+have to wait for the download of step k-1, which shares its slot); nothing is cached between steps -- every step
+copies its own inputs, rebuilds its neighbour plan and copies its own outputs.  Keep at most `depth - 1` steps
+un-fetched: submit() reuses the slot of step k - depth.
 """
 from __future__ import annotations
 
@@ -18,7 +20,7 @@ from .ops import NeighborPlan, conv3p_backward, conv3p_forward, parse_stride, pa
 
 class HostConv3p:
     def __init__(self, B: int, N: int, Cin: int, Cout: int, stride, voxel_size, device=None,
-                 capacity: Optional[int] = None, depth: int = 2):
+                 capacity: Optional[int] = None, depth: int = 3):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.shape = (B, N, Cin, Cout)
         self.stride, self.voxel = parse_stride(stride), parse_voxel(voxel_size)

@@ -14,6 +14,8 @@ hand-written sm_100a CUDA behind the C ABI of ``include/conv3p_b200.h``.  There 
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Optional, Sequence
 
@@ -251,6 +253,10 @@ def conv3p_forward(plan: NeighborPlan, input: torch.Tensor, kernel: torch.Tensor
     return out
 
 
+# upper bound on the G store a backward call may allocate (3.6 GB at 64 x 4096 points, Cout = 128)
+G_STORE_LIMIT_BYTES = int(os.environ.get("CONV3P_G_STORE_LIMIT_GB", "32")) << 30
+
+
 def conv3p_backward(plan: NeighborPlan, grad_output: torch.Tensor, input: torch.Tensor,
                     kernel: torch.Tensor, need_input_grad: bool = True,
                     need_filter_grad: bool = True):
@@ -271,6 +277,11 @@ def conv3p_backward(plan: NeighborPlan, grad_output: torch.Tensor, input: torch.
         if need_input_grad else None
     gf = torch.empty_like(kernel) if need_filter_grad else None
     nscratch = L.conv3p_scratch_bytes(plan.geom, Cin, Cout)
+    if need_input_grad and need_filter_grad:
+        # room for the G store (27*Cout floats per point) lets the two gradient kernels share one gather
+        nshared = L.conv3p_backward_scratch_bytes(plan.geom, Cin, Cout)
+        if nshared - nscratch <= G_STORE_LIMIT_BYTES:
+            nscratch = nshared
     scratch = torch.empty(nscratch, dtype=torch.uint8, device=plan.device)
     with torch.cuda.device(plan.device):
         _lib.check(L.conv3p_backward_f32(plan.geom, _ptr(plan.buffer), _ptr(grad_output), _ptr(input),

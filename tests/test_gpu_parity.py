@@ -449,3 +449,30 @@ def test_small_channel_engine_and_tile_engine_match_oracle(port, Cin, Cout, stri
         assert_close_scaled(gf.cpu().numpy(), r[4], r[5], RTOL, ATOL, f"grad_filter[{eng}]")
         res[eng] = y
     assert res["simt"].shape == res["tile"].shape
+
+
+@pytest.mark.parametrize("B,N,stride,dist,q", [(3, 1500, 1, "room", 0.0), (2, 2048, 2, "room", 0.05),
+                                               (4, 700, 1, "sphere", 0.0), (1, 129, 3, "cube", 0.0)])
+def test_shared_gather_of_the_two_gradients_is_bit_identical(B, N, stride, dist, q):
+    """With both gradients requested the grad_input kernel leaves its per-(point, cell) aggregates of grad_output in
+    the G store and the grad_filter kernel reads them back instead of walking the backward lists again: same
+    members, same order of additions -> bit-identical to the un-shared kernels (engine bit 256) and to a call that
+    asks for grad_filter alone."""
+    from pointwise_b200 import NeighborPlan, _lib, conv3p_backward
+    Cin, Cout = 64, 128
+    pr = make_problem(B, N, Cin, Cout, dist, seed=77, quantise=q or None)
+    plan = NeighborPlan(dev(pr["points"]), (stride,) * 3, V).ensure_backward()
+    g, x, w = dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"])
+    L = _lib.lib()
+    gi_s, gf_s = conv3p_backward(plan, g, x, w)
+    prev = L.conv3p_set_engine(256)
+    try:
+        gi_u, gf_u = conv3p_backward(plan, g, x, w)
+    finally:
+        L.conv3p_set_engine(prev)
+    _, gf_only = conv3p_backward(plan, g, x, w, need_input_grad=False)
+    torch.cuda.synchronize()
+    assert torch.equal(gi_s, gi_u)
+    assert torch.equal(gf_s, gf_u)
+    assert torch.equal(gf_s, gf_only)
+    assert float(gf_s.abs().max()) > 0
