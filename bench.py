@@ -190,9 +190,13 @@ def config_dict(workload, gpus, **extra):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(kernel: str, pts: int, Cin: int, Cout: int, kbar: float, kbar_b: float):
+def algorithmic_bytes(kernel: str, pts: int, Cin: int, Cout: int, kbar: float, kbar_b: float,
+                      nbins_b: float = 0.0, shared: bool = False):
     """Algorithmic bytes per launch (DESIGN.md section 'Kernels and their roofs'), gather model G of
-    SURVEY section 8d: every list entry is one index read plus one row read."""
+    SURVEY section 8d: every list entry is one index read plus one row read.  With the shared gather (`shared`:
+    both gradients on the tensor-core kernels) the grad_input kernel also writes one Cout-wide row per non-empty
+    (point, cell) slot (nbins_b of them per point) and the grad_filter kernel reads those rows back instead of
+    walking the lists."""
     nW = 27 * Cin * Cout * 4
     per_point = {
         "k_gather_contract_fwd": kbar * (4 * Cin + 4) + 27 * 4 + 8 + 16 + 4 * Cout,
@@ -208,6 +212,10 @@ def algorithmic_bytes(kernel: str, pts: int, Cin: int, Cout: int, kbar: float, k
         "k_backward_lists": 16 + kbar * (4 + 12 + 4) + 27 * 4 + kbar_b * 8,
         "k_cloud_sort": 12 + 16 + 4 + 4 * 16,
     }.get(kernel, 0.0)
+    if shared and kernel == "k_backward_input_tc":
+        per_point += nbins_b * 4 * Cout
+    if shared and kernel == "k_backward_filter_tc":
+        per_point = nbins_b * (4 * Cout + 8) + 27 * 4 + 8 + 16 + 4 * Cin
     fixed = nW if kernel.startswith("k_gather") or kernel.endswith("_tc") or kernel.startswith("k_small_") else (2 * nW if kernel.startswith("k_backward_filter") else 0)
     return per_point * pts + fixed
 
@@ -252,6 +260,9 @@ def gpu_arm(args):
     kbar = st.total_pairs / pts
     kbar_b = st.backward_pairs / pts
     nbins = float((probe.count_table > 0).sum().item()) / pts
+    nbins_b = float((probe.backward_count_table > 0).sum().item()) / pts
+    # both gradients of this shape run on the tensor-core kernels with the shared gather (G store)?
+    shared = bool(L.conv3p_backward_scratch_bytes(probe.geom, Cin, Cout) > L.conv3p_scratch_bytes(probe.geom, Cin, Cout))
     del probe
 
     def barrier():
@@ -344,21 +355,22 @@ def gpu_arm(args):
     kernels = {}
     for name, (n, total) in sorted(kern.items(), key=lambda kv: -kv[1][1]):
         avg_ms = total / n
-        ab = algorithmic_bytes(name, pts, Cin, Cout, kbar, kbar_b)
+        ab = algorithmic_bytes(name, pts, Cin, Cout, kbar, kbar_b, nbins_b, shared)
         kernels[name] = {"launches_per_step": n // args.steps, "avg_ms": round(avg_ms, 4),
                          "share_of_step": round(total / args.steps / ms_step, 4),
                          "algorithmic_gbs": round(ab / (avg_ms * 1e-3) / 1e9, 1)}
     if top:
         n, total = kern[top]
         avg_s = total / n * 1e-3
-        ab = algorithmic_bytes(top, pts, Cin, Cout, kbar, kbar_b)
+        ab = algorithmic_bytes(top, pts, Cin, Cout, kbar, kbar_b, nbins_b, shared)
         flops = 2.0 * 27 * Cin * Cout * pts
         roof = {"kernel": top, "bound": "hbm", "achieved": ab / avg_s / 1e9, "peak": pk["hbm_gbs"],
                 "unit": "GB/s", "frac": ab / avg_s / 1e9 / pk["hbm_gbs"],
                 "traffic": traffic.get(top, {}).get("dram_bytes_per_launch"),
                 "algorithmic_bytes_per_launch": ab,
                 "peak_source": pk["source"] + " (MEASURED_PEAKS.json hbm_gbs)",
-                "model": "gather model G (SURVEY 8d): list entries x (index + row bytes) + per-point I/O",
+                "model": "gather model G (SURVEY 8d): list entries x (index + row bytes) + per-point I/O"
+                         + (" + G-store rows" if shared else ""),
                 "dense_tflops": flops / avg_s / 1e12,
                 "frac_fp32_simt_peak_74.4": flops / avg_s / 1e12 / 74.4}
     line = {
@@ -366,7 +378,8 @@ def gpu_arm(args):
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args.workload, world, mean_neighbours=round(kbar, 2),
-                              mean_backward_pairs=round(kbar_b, 2), mean_nonempty_cells=round(nbins, 2)),
+                              mean_backward_pairs=round(kbar_b, 2), mean_nonempty_cells=round(nbins, 2),
+                              mean_nonempty_backward_cells=round(nbins_b, 2), shared_backward_gather=shared),
         "clocks": clocks,
         "e2e": {"value": B_global * N / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "wall_ms_per_step": wall_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

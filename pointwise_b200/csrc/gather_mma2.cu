@@ -140,41 +140,51 @@ k_group_items(const int* __restrict__ cnt, const long long* __restrict__ begin, 
   for (int e = r; e < C3P_NCELL * ROWS / 2; e += ROWS) dst[e] = src[e];
 }
 
-template <int NKC, bool WEIGHTED>
+// Barrier slots of k_gather_mma2 in one shared array, addressed as bars + 8 * index.
+enum {
+  G2B_A_FULL = 0, G2B_A_EMPTY = G2B_A_FULL + G2_MAX_NAS, G2B_W_FULL = G2B_A_EMPTY + G2_MAX_NAS,
+  G2B_W_EMPTY = G2B_W_FULL + G2_MAX_NWU, G2B_IT_FULL = G2B_W_EMPTY + G2_MAX_NWU, G2B_IT_EMPTY = G2B_IT_FULL + G2_NIS,
+  G2B_ACC_FULL = G2B_IT_EMPTY + G2_NIS, G2B_COUNT
+};
+
+template <int NKC, bool WEIGHTED, bool TIMED>
 __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Nout = a.Nout, NAS = a.NAS, NWU = a.NWU;
   const uint32_t unit_bytes = (uint32_t)Nout * PANEL_ROW_BYTES;       // hi (or lo) half of a weight panel
-  unsigned char* a_base = smem;                                       // NAS stages
-  unsigned char* w_base = a_base + (size_t)NAS * G2_A_STAGE;          // NWU units
-  uint2* items = reinterpret_cast<uint2*>(w_base + (size_t)NWU * unit_bytes);  // [NIS][128]
-  int* rowid = reinterpret_cast<int*>(items + G2_NIS * 128);          // [Tmax * 128]
-  __shared__ uint64_t a_full[G2_MAX_NAS], a_empty[G2_MAX_NAS], w_full[G2_MAX_NWU], w_empty[G2_MAX_NWU],
-      it_full[G2_NIS], it_empty[G2_NIS], acc_full;
+  __shared__ uint64_t bars[G2B_COUNT];
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned active[C3P_NCELL];  // bit t: sub-tile t of the chunk has members in cell f
   __shared__ int hdr[G2_NIS];             // group in the slot: K batch | sub-tile << 8 | cell << 16, or G2_END
+  // Shared-window addresses, converted once (see tc_common.cuh): operand ring | weight units | item lists | rows
+  const uint32_t s_a = smem_u32_once(smem);                              // NAS stages
+  const uint32_t s_w = s_a + (uint32_t)NAS * G2_A_STAGE;              // NWU units
+  const uint32_t s_items = s_w + (uint32_t)NWU * unit_bytes;          // [NIS][128] uint2
+  const uint32_t s_bars = smem_u32_once(bars), s_hdr = smem_u32_once(hdr);
+  int* rowid = reinterpret_cast<int*>(smem + (size_t)NAS * G2_A_STAGE + (size_t)NWU * unit_bytes +
+                                      G2_NIS * 128 * sizeof(uint2));  // [Tmax * 128]
+  auto bar = [&](int which, int i) -> uint32_t { return s_bars + 8u * (uint32_t)(which + i); };
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool timed = (a.debug & 32) && tid == 0;
+  const bool timed = TIMED && tid == 0;
   long long tk = timed ? clock64() : 0;
   unsigned ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define G2_PHASE(i) do { if (timed) { const long long t_ = clock64(); ph[i] += (unsigned)(t_ - tk); tk = t_; } } while (0)
+#define G2_PHASE(i) do { if (TIMED && timed) { const long long t_ = clock64(); ph[i] += (unsigned)(t_ - tk); tk = t_; } } while (0)
 
   if (warp == G2_NPW && lane == 0) {
     for (int i = 0; i < NAS; ++i) {
-      mbar_init(&a_full[i], G2_NPW);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&bars[G2B_A_FULL + i], G2_NPW);
+      mbar_init(&bars[G2B_A_EMPTY + i], 1);
     }
     for (int i = 0; i < NWU; ++i) {
-      mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], 1);
+      mbar_init(&bars[G2B_W_FULL + i], 1);
+      mbar_init(&bars[G2B_W_EMPTY + i], 1);
     }
     for (int i = 0; i < G2_NIS; ++i) {
-      mbar_init(&it_full[i], 1);
-      mbar_init(&it_empty[i], G2_NPW);
+      mbar_init(&bars[G2B_IT_FULL + i], 1);
+      mbar_init(&bars[G2B_IT_EMPTY + i], G2_NPW);
     }
-    mbar_init(&acc_full, 1);
+    mbar_init(&bars[G2B_ACC_FULL], 1);
     mbar_fence_init();
   }
   if (warp == G2_NPW + 1) tmem_alloc(&tmem_slot, 512);
@@ -242,22 +252,25 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
 
     if (warp < G2_NPW) {
       // =========================== producers: gather -> mean -> hi/lo -> operand panels ===================
-      // Quarter-warp q serves items (q + 4g) mod 64 and 64 + that of group g; lane l8 owns one 16-byte chunk of
+      // Quarter-warp q serves items e = (q + 4g) mod 64 and 127 - e of group g; lane l8 owns one 16-byte chunk of
       // the row segment.  Software-pipelined: the item and the list ids of the next group are fetched before
       // the rows of the current group are gathered.
       auto read_items = [&](int g_, G2Item& i0, G2Item& i1) -> int {
         const int slot = g_ & (G2_NIS - 1);
-        mbar_wait(&it_full[slot], (uint32_t)((g_ / G2_NIS) & 1));
-        const int h = hdr[slot];
+        mbar_wait(bar(G2B_IT_FULL, slot), (uint32_t)((g_ / G2_NIS) & 1));
+        const int h = lds32(s_hdr + 4u * (uint32_t)slot);
         const int e = (q + 4 * g_) & 63;
-        const uint2 u0 = items[slot * 128 + e], u1 = items[slot * 128 + 64 + e];
+        // the list is sorted by population: pairing item e with item 127 - e gives every warp one heavy and one
+        // light (or empty) block per group, so the warps of a group finish closer together
+        const uint2 u0 = lds64(s_items + (uint32_t)(slot * 128 + e) * 8u);
+        const uint2 u1 = lds64(s_items + (uint32_t)(slot * 128 + 127 - e) * 8u);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&it_empty[slot]);
+        if (lane == 0) mbar_arrive(bar(G2B_IT_EMPTY, slot));
         const bool live = h != G2_END;
         i0.pos = u0.x; i0.p = (int)(u0.y & 255u); i0.n = live ? (int)(u0.y >> 8) : 0;
         i1.pos = u1.x; i1.p = (int)(u1.y & 255u); i1.n = live ? (int)(u1.y >> 8) : 0;
-        i0.inv = WEIGHTED ? 0.f : __fdividef(1.f, (float)i0.n);
-        i1.inv = WEIGHTED ? 0.f : __fdividef(1.f, (float)i1.n);
+        i0.inv = WEIGHTED ? 0.f : rcp_approx((float)i0.n);
+        i1.inv = WEIGHTED ? 0.f : rcp_approx((float)i1.n);
         i0.w = 0.f; i1.w = 0.f;
         g2_prefetch<WEIGHTED>(i0, a.rows, a.weights, 0, l8, max_row);
         g2_prefetch<WEIGHTED>(i1, a.rows, a.weights, 0, l8, max_row);
@@ -290,14 +303,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
         }
         G2_PHASE(5);
         // the ring stages of this group must have been drained by the tensor core
-        unsigned char* stage[NKC];
+        uint32_t stage[NKC];
         {
           int sl = p_aslot;
           uint32_t wr = p_awrap;
 #pragma unroll
           for (int kc = 0; kc < NKC; ++kc) {
-            if (wr >= 1) mbar_wait(&a_empty[sl], (wr - 1) & 1u);
-            stage[kc] = a_base + (size_t)sl * G2_A_STAGE;
+            if (wr >= 1) mbar_wait(bar(G2B_A_EMPTY, sl), (wr - 1) & 1u);
+            stage[kc] = s_a + (uint32_t)sl * G2_A_STAGE;
             if (++sl == NAS) { sl = 0; ++wr; }
           }
         }
@@ -325,8 +338,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int kc = 0; kc < NKC; ++kc) {
-              *reinterpret_cast<float4*>(stage[kc] + o) = z;
-              *reinterpret_cast<float4*>(stage[kc] + o + 128 * PANEL_ROW_BYTES) = z;
+              sts128(stage[kc] + o, z);
+              sts128(stage[kc] + o + 128 * PANEL_ROW_BYTES, z);
             }
           }
         }
@@ -336,7 +349,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
           int sl = p_aslot;
 #pragma unroll
           for (int kc = 0; kc < NKC; ++kc) {
-            mbar_arrive(&a_full[sl]);
+            mbar_arrive(bar(G2B_A_FULL, sl));
             if (++sl == NAS) sl = 0;
           }
         }
@@ -350,7 +363,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
       ++p_g;  // the END slot
       if (timed) { tk = clock64(); ph[1] += (unsigned)(tk - tl); }
       // =========================== epilogue: TMEM -> registers -> global ==============================
-      mbar_wait(&acc_full, (uint32_t)(chunk & 1));
+      mbar_wait(bar(G2B_ACC_FULL, 0), (uint32_t)(chunk & 1));
       tc_fence_after_sync();
       G2_PHASE(2);
       for (int task = warp; task < 4 * T; task += G2_NPW) {
@@ -390,7 +403,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
       // a weight panel is needed 512 MMA cycles after its hi half and the hi unit is released before the lo unit.
       if (lane == 0) {
         const uint32_t idesc = make_idesc_tf32(128, Nout);
-        const uint64_t a_desc0 = make_smem_desc(smem_u32(a_base)), w_desc0 = make_smem_desc(smem_u32(w_base));
+        const uint64_t a_desc0 = make_smem_desc(s_a), w_desc0 = make_smem_desc(s_w);
         const uint64_t a_lo_off = (uint64_t)((128 * PANEL_ROW_BYTES) >> 4);
         const uint64_t a_step = (uint64_t)(G2_A_STAGE >> 4), w_step = (uint64_t)(unit_bytes >> 4);
         unsigned started = 0;
@@ -413,8 +426,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
               started |= 1u << t;
 #pragma unroll
               for (int kc = 0; kc < NKC; ++kc) {
-                if (t == t_first) mbar_wait(&w_full[us[2 * kc]], up[2 * kc]);
-                mbar_wait(&a_full[m_aslot], m_aphase);
+                if (t == t_first) mbar_wait(bar(G2B_W_FULL, us[2 * kc]), up[2 * kc]);
+                mbar_wait(bar(G2B_A_FULL, m_aslot), m_aphase);
                 tc_fence_after_sync();
                 const uint64_t dah = a_desc0 + (uint64_t)m_aslot * a_step, dal = dah + a_lo_off;
                 const uint64_t dwh = w_desc0 + (uint64_t)us[2 * kc] * w_step;
@@ -426,9 +439,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
                   mma_tf32(d, dal + adv, dwh + adv, idesc, 1u);
                   acc_flag = 1u;
                 }
-                if (t == t_last) mma_commit(&w_empty[us[2 * kc]]);
+                if (t == t_last) mma_commit(bar(G2B_W_EMPTY, us[2 * kc]));
                 if (t == t_first) {
-                  mbar_wait(&w_full[us[2 * kc + 1]], up[2 * kc + 1]);
+                  mbar_wait(bar(G2B_W_FULL, us[2 * kc + 1]), up[2 * kc + 1]);
                   tc_fence_after_sync();
                 }
 #pragma unroll
@@ -436,14 +449,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
                   const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
                   mma_tf32(d, dah + adv, dwl + adv, idesc, 1u);
                 }
-                mma_commit(&a_empty[m_aslot]);
-                if (t == t_last) mma_commit(&w_empty[us[2 * kc + 1]]);
+                mma_commit(bar(G2B_A_EMPTY, m_aslot));
+                if (t == t_last) mma_commit(bar(G2B_W_EMPTY, us[2 * kc + 1]));
                 if (++m_aslot == NAS) { m_aslot = 0; m_aphase ^= 1u; }
               }
             }
           }
         }
-        mma_commit(&acc_full);
+        mma_commit(bar(G2B_ACC_FULL, 0));
       }
     } else if (warp == G2_NPW + 1) {
       // =========================== weight loader (one thread) =========================================
@@ -452,10 +465,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
         for (int f = 0; f < C3P_NCELL; ++f) {
           if (!active[f]) continue;
           for (int u = 0; u < units_per_cell; ++u) {
-            if (l_wrap >= 1) mbar_wait(&w_empty[l_slot], (l_wrap - 1) & 1u);
-            mbar_arrive_expect_tx(&w_full[l_slot], unit_bytes);
-            bulk_copy_g2s(w_base + (size_t)l_slot * unit_bytes,
-                          a.wp + ((size_t)f * units_per_cell + u) * unit_bytes, unit_bytes, &w_full[l_slot]);
+            if (l_wrap >= 1) mbar_wait(bar(G2B_W_EMPTY, l_slot), (l_wrap - 1) & 1u);
+            mbar_arrive_expect_tx(bar(G2B_W_FULL, l_slot), unit_bytes);
+            bulk_copy_g2s(s_w + (uint32_t)l_slot * unit_bytes,
+                          a.wp + ((size_t)f * units_per_cell + u) * unit_bytes, unit_bytes, bar(G2B_W_FULL, l_slot));
             if (++l_slot == NWU) { l_slot = 0; ++l_wrap; }
           }
         }
@@ -465,7 +478,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
       if (lane == 0) {
         auto acquire = [&]() -> int {
           const int slot = i_g & (G2_NIS - 1), use = i_g / G2_NIS;
-          if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
+          if (use >= 1) mbar_wait(bar(G2B_IT_EMPTY, slot), (uint32_t)((use - 1) & 1));
           ++i_g;
           return slot;
         };
@@ -477,15 +490,15 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
               if (!((act >> t) & 1u)) continue;
               const int slot = acquire();
               hdr[slot] = kb | (t << 8) | (f << 16);
-              mbar_arrive_expect_tx(&it_full[slot], 128 * sizeof(uint2));
-              bulk_copy_g2s(items + slot * 128, a.g_items + ((sub0 + t) * C3P_NCELL + f) * 128,
-                            128 * sizeof(uint2), &it_full[slot]);
+              mbar_arrive_expect_tx(bar(G2B_IT_FULL, slot), 128 * sizeof(uint2));
+              bulk_copy_g2s(s_items + (uint32_t)slot * 128 * 8, a.g_items + ((sub0 + t) * C3P_NCELL + f) * 128,
+                            128 * sizeof(uint2), bar(G2B_IT_FULL, slot));
             }
           }
         }
         const int slot = acquire();
         hdr[slot] = G2_END;
-        mbar_arrive(&it_full[slot]);
+        mbar_arrive(bar(G2B_IT_FULL, slot));
       }
     }
     // the next chunk overwrites the row table, the group masks and (through the MMAs) the accumulators
@@ -493,7 +506,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
     __syncthreads();
     tc_fence_after_sync();
   }
-  if (timed)
+  if (TIMED && timed)
     for (int i = 0; i < 8; ++i) atomicAdd(&g2_phase_cycles[i], (unsigned long long)ph[i]);
   if (warp == G2_NPW + 1) tmem_dealloc(tmem, 512);
 }
@@ -613,8 +626,12 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
     C3P_LAUNCH_CHECK(name);
     return CONV3P_OK;
   };
-  if (c.NKC == 1) return weighted ? launch(k_gather_mma2<1, true>) : launch(k_gather_mma2<1, false>);
-  return weighted ? launch(k_gather_mma2<2, true>) : launch(k_gather_mma2<2, false>);
+  if (a.debug & 32) {   // phase timers compiled in (tools/engine_timing.py)
+    if (c.NKC == 1) return weighted ? launch(k_gather_mma2<1, true, true>) : launch(k_gather_mma2<1, false, true>);
+    return weighted ? launch(k_gather_mma2<2, true, true>) : launch(k_gather_mma2<2, false, true>);
+  }
+  if (c.NKC == 1) return weighted ? launch(k_gather_mma2<1, true, false>) : launch(k_gather_mma2<1, false, false>);
+  return weighted ? launch(k_gather_mma2<2, true, false>) : launch(k_gather_mma2<2, false, false>);
 }
 
 }  // namespace c3p

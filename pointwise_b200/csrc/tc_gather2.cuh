@@ -48,18 +48,22 @@ __device__ __forceinline__ void g2_gather(float4 (&acc)[NKC], G2Item& it, int nm
                                           int l8, unsigned max_row) {
 #pragma unroll
   for (int kc = 0; kc < NKC; ++kc) acc[kc] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* base = src + col + l8 * 4;
+  // row address = base + id * (row bytes): one IMAD.WIDE.U32 per member
+  const char* base = reinterpret_cast<const char*>(src + col + l8 * 4);
+  const unsigned row_bytes = (unsigned)Csrc * 4u;
   for (int m0 = 0; m0 < nmax; m0 += M) {
     if (m0 && !(m0 & 7)) g2_prefetch<WEIGHTED>(it, rows, weights, m0, l8, max_row);
     float4 v[M][NKC];
     float wv[M];
+    // (Predicated loads into zeroed registers instead of weight-0 re-reads were measured slower: 0.91 against
+    // 0.87 ms forward -- the extra zeroing instructions cost more than the saved L1 wavefronts.)
 #pragma unroll
     for (int m = 0; m < M; ++m) {
       const int id = __shfl_sync(C3P_FULL_MASK, it.ids, (m0 + m) & 7, 8);
       float w = it.inv;
       if (WEIGHTED) w = __shfl_sync(C3P_FULL_MASK, it.w, (m0 + m) & 7, 8);
       wv[m] = (m0 + m < it.n) ? w : 0.f;
-      const float* p = base + (size_t)id * Csrc;
+      const float* p = reinterpret_cast<const float*>(base + (size_t)(unsigned)id * row_bytes);
 #pragma unroll
       for (int kc = 0; kc < NKC; ++kc) v[m][kc] = ldg4(p + kc * PANEL_K);
     }
@@ -68,6 +72,22 @@ __device__ __forceinline__ void g2_gather(float4 (&acc)[NKC], G2Item& it, int nm
 #pragma unroll
       for (int kc = 0; kc < NKC; ++kc) fma4(acc[kc], wv[m], v[m][kc]);
   }
+}
+
+// Same on a 32-bit shared-window address.
+__device__ __forceinline__ void g2_store_split(uint32_t dst, uint32_t lo_offset, const float4& v) {
+  const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  const float2 l0 = __fadd2_rn(make_float2(v.x, v.y), make_float2(-h.x, -h.y));
+  const float2 l1 = __fadd2_rn(make_float2(v.z, v.w), make_float2(-h.z, -h.w));
+  sts128(dst, h);
+  sts128(dst + lo_offset, make_float4(l0.x, l0.y, l1.x, l1.y));
+}
+
+// 1 / x for x >= 1 (member counts): one MUFU.RCP, within 1 ulp.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 // Writes the TF32 hi part of v at `dst` and the lo part `lo_offset` bytes further (16-byte chunk).

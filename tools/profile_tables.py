@@ -10,11 +10,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
-NAMES = {"k_gather_mma_tc<2, 0>": "k_forward_tc", "k_gather_mma_tc<2, 1>": "k_backward_input_tc",
-         "k_gather_mma_tc<1, 0>": "k_forward_tc", "k_gather_mma_tc<1, 1>": "k_backward_input_tc",
-         "k_gather_mma2<2, 0>": "k_forward_tc", "k_gather_mma2<2, 1>": "k_backward_input_tc",
-         "k_gather_mma2<1, 0>": "k_forward_tc", "k_gather_mma2<1, 1>": "k_backward_input_tc",
-         "k_backward_filter2": "k_backward_filter_tc", "k_backward_fused": "k_backward_fused"}
+def display_name(kernel_name: str) -> str:
+    """ncu kernel name -> the name bench.py's per-kernel timers use."""
+    key = kernel_name.split("(")[0].replace("void ", "").replace("c3p::", "")
+    if key.startswith("k_gather_mma"):
+        args = key[key.index("<") + 1:key.index(">")].replace(" ", "").split(",")
+        return "k_backward_input_tc" if args[1] in ("1", "true") else "k_forward_tc"
+    if key.startswith("k_backward_filter2") or key.startswith("k_backward_filter_tc"):
+        return "k_backward_filter_tc"
+    return key
 
 
 def ncu_raw(rep):
@@ -33,10 +37,7 @@ def main():
     lines.append("|---|---|---|---|---|---|---|---|---|---|")
     for r in rows:
         kn = g(r, "Kernel Name")
-        key = kn.split("(")[0].replace("void ", "")
-        for a, b in NAMES.items():
-            if a in kn:
-                key = b
+        key = display_name(kn)
         rd = float(g(r, "dram__bytes_read.sum").replace(",", "")) * conv[units[hdr.index("dram__bytes_read.sum")]]
         wr = float(g(r, "dram__bytes_write.sum").replace(",", "")) * conv[units[hdr.index("dram__bytes_write.sum")]]
         if key in traffic:   # several launches of one kernel (k_group_items): keep the first
