@@ -120,6 +120,26 @@ int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float*
                        const float* filter, int Cin, int Cout, float* output, void* scratch,
                        size_t scratch_bytes, conv3p_stream_t stream);
 
+/* Forward with the epilogue the reference's networks apply right after every Conv3p, fused:
+ *   - `activation` = CONV3P_ACT_SELU stores selu(Conv3p(...)) -- `selu(conv3p(...))` at
+ *     scene_seg/pointcnn_scene_seg_acsd.py:35-36, selu.py:22-26 -- instead of a second pass over the output;
+ *   - rows of `input` and `output` may sit inside wider row-major buffers (`*_row_stride` floats from one row to
+ *     the next, >= the channel count; 0 = dense), so the four 9-channel layers can write straight into the
+ *     [B,N,36] concat buffer (:56) and read their predecessor's slice of it.
+ * The tensor-core engine needs 16-byte aligned rows (strides % 4 == 0, aligned base pointers); other layouts run on
+ * the fp32 engines.  Everything else as conv3p_forward_f32. */
+enum { CONV3P_ACT_NONE = 0, CONV3P_ACT_SELU = 1 };
+int conv3p_forward_ex_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
+                          long long input_row_stride, const float* filter, int Cin, int Cout, float* output,
+                          long long output_row_stride, int activation, void* scratch, size_t scratch_bytes,
+                          conv3p_stream_t stream);
+
+/* out[r, c] = grad[r, c] * selu'(x) expressed through the ACTIVATED value y = selu(x) the forward stored:
+ * scale for y > 0, y + scale*alpha otherwise.  y and grad rows may be strided (floats; 0 = dense); out is dense
+ * [rows, C].  The backward of the fused epilogue: feed `out` to conv3p_backward_f32 as grad_output. */
+int conv3p_selu_backward_f32(const float* y, long long y_row_stride, const float* grad, long long grad_row_stride,
+                             float* out, long long rows, int C, conv3p_stream_t stream);
+
 /* grad_input[B,N,Cin], grad_filter[27,Cin,Cout]; follows tf_conv3p_atrous.cpp:622-716.
  * Either output pointer may be NULL to skip it.  grad_filter is reduced in a fixed order
  * (deterministic; the reference's OpenMP/atomicAdd reductions are not). */

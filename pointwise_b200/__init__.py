@@ -10,8 +10,8 @@ Everything computes in hand-written CUDA behind the C ABI of include/conv3p_b200
 or PyTorch fallback.
 """
 from .ops import (NeighborPlan, conv3p, conv3p_backward, conv3p_forward, conv3p_grad,  # noqa: F401
-                  launch_count, set_engine)
+                  launch_count, selu_backward, set_engine)
 from ._lib import Conv3pError  # noqa: F401
 
 __all__ = ["conv3p", "conv3p_grad", "conv3p_forward", "conv3p_backward", "NeighborPlan",
-           "Conv3pError", "launch_count", "set_engine"]
+           "Conv3pError", "launch_count", "selu_backward", "set_engine"]

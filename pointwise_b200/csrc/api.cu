@@ -147,6 +147,19 @@ static conv3p_geom_t make_geom(int B, int N, const int stride[3], float voxel, l
   return g;
 }
 
+// out[r, c] = grad[r, c] * selu'(x), from the activated value y = selu(x): scale if y > 0 else y + scale * alpha
+__global__ void k_selu_backward(const float* __restrict__ y, long long ys, const float* __restrict__ g, long long gs,
+                                float* __restrict__ out, long long rows, int C) {
+  const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+  const long long total = rows * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / C;
+    const int c = (int)(e - r * C);
+    const float yv = __ldg(y + r * ys + c);
+    out[e] = __ldg(g + r * gs + c) * (yv > 0.f ? scale : yv + scale * alpha);
+  }
+}
+
 }  // namespace c3p
 
 using namespace c3p;
@@ -291,23 +304,62 @@ size_t conv3p_backward_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cou
   return base + g_store_bytes(geom, Cin, Cout);
 }
 
-int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
-                       const float* filter, int Cin, int Cout, float* output, void* scratch,
-                       size_t scratch_bytes, conv3p_stream_t stream) {
+int conv3p_forward_ex_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
+                          long long input_row_stride, const float* filter, int Cin, int Cout, float* output,
+                          long long output_row_stride, int activation, void* scratch, size_t scratch_bytes,
+                          conv3p_stream_t stream) {
   int st = check_channels(Cin, Cout);
   if (st) return st;
+  if (activation != CONV3P_ACT_NONE && activation != CONV3P_ACT_SELU) return CONV3P_ERR_INVALID_ARGUMENT;
+  if ((input_row_stride && input_row_stride < Cin) || (output_row_stride && output_row_stride < Cout))
+    return CONV3P_ERR_INVALID_ARGUMENT;
   PlanView v;
   st = make_view(geom, plan, conv3p_plan_bytes(geom), &v);
   if (st) return st;
   if ((long long)geom->B * geom->N == 0) return CONV3P_OK;
   if (!input || !filter || !output) return CONV3P_ERR_INVALID_ARGUMENT;
-  if (engine() != 1 && forward_tc_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
+  RowIO io;
+  io.src_stride = input_row_stride == Cin ? 0 : input_row_stride;
+  io.out_stride = output_row_stride == Cout ? 0 : output_row_stride;
+  io.activation = activation;
+  const long long ls = io.src_stride ? io.src_stride : Cin, lo = io.out_stride ? io.out_stride : Cout;
+  const bool rows_aligned = ls % 4 == 0 && lo % 4 == 0 && reinterpret_cast<uintptr_t>(input) % 16 == 0 &&
+                            reinterpret_cast<uintptr_t>(output) % 16 == 0;
+  const bool dense = !io.src_stride && !io.out_stride && !io.activation;
+  // tensor cores: the second-generation kernel takes strided rows and the epilogue, the first generation dense rows only
+  if (engine() != 1 && forward_tc_supported(geom->N, geom->pair_capacity, Cin, Cout) && rows_aligned &&
+      (dense || (!(engine() & 128) && gather_mma2_supported(geom->N, geom->pair_capacity, Cin, Cout)))) {
     if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
-    return launch_forward_tc(geom, v, input, filter, Cin, Cout, output, scratch, scratch_bytes, stream);
+    return launch_forward_tc(geom, v, input, filter, Cin, Cout, output, scratch, scratch_bytes, stream, io);
   }
   if (engine() != 3 && small_channels_supported(Cin, Cout))
-    return launch_forward_small(geom, v, input, filter, Cin, Cout, output, stream);
-  return launch_forward_simt(geom, v, input, filter, Cin, Cout, output, stream);
+    return launch_forward_small(geom, v, input, filter, Cin, Cout, output, stream, io);
+  return launch_forward_simt(geom, v, input, filter, Cin, Cout, output, stream, io);
+}
+
+int conv3p_forward_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
+                       const float* filter, int Cin, int Cout, float* output, void* scratch,
+                       size_t scratch_bytes, conv3p_stream_t stream) {
+  return conv3p_forward_ex_f32(geom, plan, input, 0, filter, Cin, Cout, output, 0, CONV3P_ACT_NONE, scratch,
+                               scratch_bytes, stream);
+}
+
+int conv3p_selu_backward_f32(const float* y, long long y_row_stride, const float* grad, long long grad_row_stride,
+                             float* out, long long rows, int C, conv3p_stream_t stream) {
+  if (rows < 0 || C < 1) return CONV3P_ERR_INVALID_ARGUMENT;
+  if (rows == 0) return CONV3P_OK;
+  if (!y || !grad || !out) return CONV3P_ERR_INVALID_ARGUMENT;
+  const long long ys = y_row_stride ? y_row_stride : C, gs = grad_row_stride ? grad_row_stride : C;
+  if (ys < C || gs < C) return CONV3P_ERR_INVALID_ARGUMENT;
+  const long long total = rows * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  {
+    LaunchTimer timer_("k_selu_backward", stream);
+    k_selu_backward<<<(unsigned)blocks, 256, 0, stream>>>(y, ys, grad, gs, out, rows, C);
+  }
+  C3P_LAUNCH_CHECK("k_selu_backward");
+  return CONV3P_OK;
 }
 
 int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float* grad_output,

@@ -200,7 +200,7 @@ int launch_backward_filter_simt(const conv3p_geom_t* g, const PlanView& v, const
   const size_t smem = sizeof(float) * (size_t)BF_P * (c.KB + c.CB);
   dim3 grid(C3P_NCELL, c.S, c.nKB * c.nCB);
   if (c.TK == 4) {
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default too)
       C3P_CUDA(cudaFuncSetAttribute(k_backward_filter<4, 8>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {

@@ -28,6 +28,16 @@ struct PlanView {
 
 namespace c3p {
 
+// Row layout and epilogue of a forward call (conv3p_forward_ex_f32): rows of `input` / `output` may live inside wider
+// buffers (row strides in floats; 0 = dense), and the output may pass through SELU before it is stored --
+// the activation that follows every Conv3p of the reference's networks (scene_seg/pointcnn_scene_seg_acsd.py:35-36)
+// and the concat of their outputs (:56) then cost no extra pass over memory.
+struct RowIO {
+  long long src_stride = 0;   // floats between consecutive gathered rows
+  long long out_stride = 0;   // floats between consecutive output rows
+  int activation = 0;         // CONV3P_ACT_NONE / CONV3P_ACT_SELU
+};
+
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 int compute_layout(const conv3p_geom_t* g, conv3p_plan_layout_t* L);
@@ -54,7 +64,8 @@ int launch_neighbor_search(const conv3p_geom_t* g, const PlanView& v, cudaStream
 int launch_backward_lists(const conv3p_geom_t* g, const float* points, const PlanView& v,
                           cudaStream_t stream);
 int launch_forward_simt(const conv3p_geom_t* g, const PlanView& v, const float* input,
-                        const float* filter, int Cin, int Cout, float* output, cudaStream_t stream);
+                        const float* filter, int Cin, int Cout, float* output, cudaStream_t stream,
+                        const RowIO& io = RowIO());
 int launch_backward_input_simt(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
                                const float* filter, int Cin, int Cout, float* grad_input,
                                cudaStream_t stream);
@@ -74,7 +85,7 @@ int launch_prep_weight_panels(const float* filter, void* wp, int Cin, int Cout, 
                               cudaStream_t stream);
 int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* input, const float* filter,
                       int Cin, int Cout, float* output, void* scratch, size_t scratch_bytes,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const RowIO& io = RowIO());
 
 // second-generation gather + MMA kernel (gather_mma2.cu); engine bit 128 selects the first generation instead
 bool gather_mma2_supported(int N, long long capacity, int Csrc, int Nout);
@@ -95,7 +106,7 @@ int launch_group_items(const conv3p_geom_t* g, const PlanView& v, bool backward_
                        const GroupItems& gi, cudaStream_t stream);
 int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* src, const void* wp, int Csrc,
                        int Nout, float* out, bool weighted, void* scratch, size_t scratch_bytes, const char* name,
-                       cudaStream_t stream, float* g_store = nullptr);
+                       cudaStream_t stream, float* g_store = nullptr, const RowIO& io = RowIO());
 // scratch layout of one forward / backward call: [weight panel images | work-item lists | grad_filter partials]
 size_t tc_items_bytes(const conv3p_geom_t* g, int Cin, int Cout);
 
@@ -117,7 +128,7 @@ bool small_channels_supported(int Cin, int Cout);
 bool small_backward_filter_supported(int Cin, int Cout);
 size_t backward_filter_small_scratch_bytes(int Cin, int Cout);
 int launch_forward_small(const conv3p_geom_t* g, const PlanView& v, const float* input, const float* filter,
-                         int Cin, int Cout, float* output, cudaStream_t stream);
+                         int Cin, int Cout, float* output, cudaStream_t stream, const RowIO& io = RowIO());
 int launch_backward_input_small(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
                                 const float* filter, int Cin, int Cout, float* grad_input, cudaStream_t stream);
 int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
@@ -190,6 +201,15 @@ __device__ __forceinline__ int tap_of_fast(float v, float lo, float voxel, float
 __device__ __forceinline__ int grid_coord(float v, float vmin, float cell, int dim) {
   int c = __float2int_rz(__fdiv_rn(__fsub_rn(v, vmin), cell));
   return max(0, min(c, dim - 1));
+}
+
+// SELU as the reference defines it (selu.py:22-26): scale * (x >= 0 ? x : alpha * (exp(x) - 1)).
+__device__ __forceinline__ float selu_f(float x) {
+  const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+  return scale * (x >= 0.f ? x : alpha * expm1f(x));
+}
+__device__ __forceinline__ float apply_activation(float x, int activation) {
+  return activation == CONV3P_ACT_SELU ? selu_f(x) : x;
 }
 
 __device__ __forceinline__ unsigned lanemask_lt() {

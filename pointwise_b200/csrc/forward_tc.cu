@@ -436,7 +436,7 @@ static int launch_gather_mma(FTArgs& a, const FTConfig& c, bool weighted, const 
 
 int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* input, const float* filter,
                       int Cin, int Cout, float* output, void* scratch, size_t scratch_bytes,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const RowIO& io) {
   FTConfig c;
   if (!ft_config(g->N, g->pair_capacity, Cin, Cout, &c, (long long)g->B * g->N)) return CONV3P_ERR_UNSUPPORTED;
   if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
@@ -445,8 +445,9 @@ int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* in
   if (!(engine() & 128) && gather_mma2_supported(g->N, g->pair_capacity, Cin, Cout)) {
     const size_t wpb = weight_panel_bytes(Cin, Cout);
     return launch_gather_mma2(g, v, input, scratch, Cin, Cout, output, false, static_cast<char*>(scratch) + wpb,
-                              scratch_bytes - wpb, "k_forward_tc", stream);
+                              scratch_bytes - wpb, "k_forward_tc", stream, nullptr, io);
   }
+  if (io.src_stride || io.out_stride || io.activation) return CONV3P_ERR_UNSUPPORTED;  // first-generation kernel: dense rows only
   FTArgs a{};
   a.src = input; a.wp = static_cast<const unsigned char*>(scratch); a.out = output;
   a.cnt = v.count_table; a.begin = v.pair_begin; a.len = v.pair_len; a.rows = v.pair_row;

@@ -32,6 +32,8 @@ struct GCArgs {
   long long capacity;
   int N, Cin, Cout;
   int Csrc, Nout;
+  long long src_stride, out_stride;  // floats between rows
+  int activation;
   int transposed;          // 0: B[kk][n] = W[f][kk][n] (forward); 1: B[kk][n] = W[f][n][kk]
   int P, nTx, nTy, KC, NoutPad;
 };
@@ -102,9 +104,9 @@ __global__ void __launch_bounds__(GC_THREADS) k_gather_contract(const GCArgs a) 
           if (a.weights) {
             const float* w = a.weights + at;
             for (int m = 0; m < n; ++m)
-              s = fmaf(__ldg(w + m), __ldg(a.src + (size_t)__ldg(r + m) * a.Csrc + kc + k), s);
+              s = fmaf(__ldg(w + m), __ldg(a.src + (size_t)__ldg(r + m) * a.src_stride + kc + k), s);
           } else {
-            for (int m = 0; m < n; ++m) s += __ldg(a.src + (size_t)__ldg(r + m) * a.Csrc + kc + k);
+            for (int m = 0; m < n; ++m) s += __ldg(a.src + (size_t)__ldg(r + m) * a.src_stride + kc + k);
             s = __fdiv_rn(s, (float)n);
           }
         }
@@ -166,10 +168,11 @@ __global__ void __launch_bounds__(GC_THREADS) k_gather_contract(const GCArgs a) 
       if (row == -1) continue;
       const bool poison = row < -1;
       if (poison) row = -2 - row;
-      float* o = a.out + (size_t)row * a.Nout + n0 + tx * TC;
+      float* o = a.out + (size_t)row * a.out_stride + n0 + tx * TC;
 #pragma unroll
       for (int j = 0; j < TC; ++j)
-        if (n0 + tx * TC + j < a.Nout) o[j] = poison ? __int_as_float(0x7fc00000) : acc[i][j];
+        if (n0 + tx * TC + j < a.Nout)
+          o[j] = poison ? __int_as_float(0x7fc00000) : apply_activation(acc[i][j], a.activation);
     }
   }
 }
@@ -188,7 +191,7 @@ static int launch_cfg(GCArgs& a, cudaStream_t stream) {
   const size_t smem = sizeof(float) * ((size_t)a.KC * a.NoutPad + (((size_t)a.P * (a.KC + 1) + 1) & ~(size_t)1)) +
                       sizeof(long long) * a.P + sizeof(int) * ((size_t)a.P * 28 + a.P);
   auto kern = k_gather_contract<TP, TC>;
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default too)
     C3P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (a.total_points + a.P - 1) / a.P;
   dim3 grid((unsigned)tiles, (unsigned)ncol);
@@ -207,13 +210,16 @@ static int launch_gc(GCArgs& a, cudaStream_t stream) {
 }
 
 int launch_forward_simt(const conv3p_geom_t* g, const PlanView& v, const float* input,
-                        const float* filter, int Cin, int Cout, float* output, cudaStream_t stream) {
+                        const float* filter, int Cin, int Cout, float* output, cudaStream_t stream,
+                        const RowIO& io) {
   GCArgs a{};
   a.src = input; a.filter = filter; a.out = output;
   a.cnt = v.count_table; a.begin = v.pair_begin; a.len = v.pair_len; a.rows = v.pair_row;
   a.weights = nullptr; a.sorted_xyzi = v.sorted_xyzi;
   a.total_points = (long long)g->B * g->N; a.capacity = g->pair_capacity;
   a.N = g->N; a.Cin = Cin; a.Cout = Cout; a.Csrc = Cin; a.Nout = Cout; a.transposed = 0;
+  a.src_stride = io.src_stride ? io.src_stride : Cin; a.out_stride = io.out_stride ? io.out_stride : Cout;
+  a.activation = io.activation;
   return launch_gc(a, stream);
 }
 
@@ -226,6 +232,7 @@ int launch_backward_input_simt(const conv3p_geom_t* g, const PlanView& v, const 
   a.weights = v.bwd_weight; a.sorted_xyzi = v.sorted_xyzi;
   a.total_points = (long long)g->B * g->N; a.capacity = g->pair_capacity;
   a.N = g->N; a.Cin = Cin; a.Cout = Cout; a.Csrc = Cout; a.Nout = Cin; a.transposed = 1;
+  a.src_stride = Cout; a.out_stride = Cin; a.activation = 0;
   return launch_gc(a, stream);
 }
 

@@ -51,6 +51,8 @@ struct G2Args {
   long long total_points, subtiles;
   int N, Csrc, Nout, nkb, T, NAS, NWU;
   int debug;  // bit 32: accumulate the phase timers below
+  long long src_stride, out_stride;  // floats between gathered rows / output rows (multiples of 4)
+  int activation;                    // epilogue: CONV3P_ACT_*
   // WEIGHTED only, optional: the aggregated rows G_f[j, :] of every non-empty (point, cell) are also written to
   // g_store[(sorted position * 27 + f) * Csrc ...], where the weight-gradient kernel picks them up instead of
   // gathering the same lists a second time (backward_filter2.cu).
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
         G2_PHASE(4);
         const int col = (hc & 255) * NKC * PANEL_K;
         float4 acc[NKC];
-        g2_gather<NKC, 4, WEIGHTED>(acc, c0, warp_max(c0.n), a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
+        g2_gather<NKC, 4, WEIGHTED>(acc, c0, warp_max(c0.n), a.src, (int)a.src_stride, col, a.rows, a.weights, l8, max_row);
         // row of G_f in the store: sorted position * 27 + cell
         float* gs = nullptr;
         if (WEIGHTED && a.g_store)
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
         }
         const int nmax1 = warp_max(c1.n);
         if (nmax1 > 0) {
-          g2_gather<NKC, 4, WEIGHTED>(acc, c1, nmax1, a.src, a.Csrc, col, a.rows, a.weights, l8, max_row);
+          g2_gather<NKC, 4, WEIGHTED>(acc, c1, nmax1, a.src, (int)a.src_stride, col, a.rows, a.weights, l8, max_row);
           if (WEIGHTED && gs && c1.n > 0) {
 #pragma unroll
             for (int kc = 0; kc < NKC; ++kc)
@@ -383,7 +385,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           if (row >= 0) {
-            float* o = a.out + (size_t)row * Nout + c0_;
+            float* o = a.out + (size_t)row * a.out_stride + c0_;
+            if (a.activation) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = apply_activation(v[j], a.activation);
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (c0_ + j < Nout) {
@@ -591,7 +597,7 @@ size_t gather_mma2_scratch_bytes(const conv3p_geom_t* g) { return group_items_by
 
 int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* src, const void* wp, int Csrc,
                        int Nout, float* out, bool weighted, void* scratch, size_t scratch_bytes, const char* name,
-                       cudaStream_t stream, float* g_store) {
+                       cudaStream_t stream, float* g_store, const RowIO& io) {
   G2Config c;
   const long long pts = (long long)g->B * g->N;
   if (!g2_config(g->N, g->pair_capacity, Csrc, Nout, &c)) return CONV3P_ERR_UNSUPPORTED;
@@ -613,6 +619,13 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
   a.nkb = c.nkb; a.T = c.T; a.NAS = c.NAS; a.NWU = c.NWU;
   a.debug = engine() >= 64 ? (engine() & ~(64 | 128 | 256)) : 0;
   a.g_store = weighted ? g_store : nullptr;
+  a.src_stride = io.src_stride ? io.src_stride : Csrc;
+  a.out_stride = io.out_stride ? io.out_stride : Nout;
+  a.activation = io.activation;
+  // 16-byte vector accesses: rows must start on 16-byte boundaries
+  if (a.src_stride % 4 || a.out_stride % 4 || reinterpret_cast<uintptr_t>(src) % 16 ||
+      reinterpret_cast<uintptr_t>(out) % 16 || a.src_stride >= (1LL << 29))
+    return CONV3P_ERR_UNSUPPORTED;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   (void)cudaGetLastError();

@@ -30,6 +30,8 @@ struct SCArgs {
   const float4* sorted_xyzi;
   long long total_points, capacity;
   int N, Cin, Cout, Csrc, Nout;
+  long long src_stride, out_stride;  // floats between rows
+  int activation;
   int transposed;          // 0: B[k][n] = W[f][k][n]; 1: B[k][n] = W[f][n][k]
 };
 
@@ -73,8 +75,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_small_gather_contract(const SCAr
         const int j0 = __ldg(r + m), j1 = __ldg(r + m + 1);
         const float w0 = a.weights ? __ldg(a.weights + at + before + m) : 1.f;
         const float w1 = a.weights ? __ldg(a.weights + at + before + m + 1) : 1.f;
-        const float* p0 = a.src + (size_t)j0 * Csrc;
-        const float* p1 = a.src + (size_t)j1 * Csrc;
+        const float* p0 = a.src + (size_t)j0 * a.src_stride;
+        const float* p1 = a.src + (size_t)j1 * a.src_stride;
         const float x00 = lane < Csrc ? __ldg(p0 + lane) : 0.f, x10 = lane < Csrc ? __ldg(p1 + lane) : 0.f;
         const float x01 = lane + 32 < Csrc ? __ldg(p0 + lane + 32) : 0.f;
         const float x11 = lane + 32 < Csrc ? __ldg(p1 + lane + 32) : 0.f;
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_small_gather_contract(const SCAr
       if (m < n) {
         const int j0 = __ldg(r + m);
         const float w0 = a.weights ? __ldg(a.weights + at + before + m) : 1.f;
-        const float* p0 = a.src + (size_t)j0 * Csrc;
+        const float* p0 = a.src + (size_t)j0 * a.src_stride;
         a0 = fmaf(w0, lane < Csrc ? __ldg(p0 + lane) : 0.f, a0);
         a1 = fmaf(w0, lane + 32 < Csrc ? __ldg(p0 + lane + 32) : 0.f, a1);
       }
@@ -101,8 +103,9 @@ __global__ void __launch_bounds__(SC_THREADS) k_small_gather_contract(const SCAr
       }
     }
     const float nanv = __int_as_float(0x7fc00000);
-    if (lane < Nout) a.out[(size_t)row * Nout + lane] = ok ? acc0 : nanv;
-    if (lane + 32 < Nout) a.out[(size_t)row * Nout + lane + 32] = ok ? acc1 : nanv;
+    if (lane < Nout) a.out[(size_t)row * a.out_stride + lane] = ok ? apply_activation(acc0, a.activation) : nanv;
+    if (lane + 32 < Nout)
+      a.out[(size_t)row * a.out_stride + lane + 32] = ok ? apply_activation(acc1, a.activation) : nanv;
   }
 }
 
@@ -220,7 +223,7 @@ bool small_backward_filter_supported(int Cin, int Cout) {
 static int launch_small_gc(SCArgs& a, const char* name, cudaStream_t stream) {
   if (a.total_points == 0) return CONV3P_OK;
   const size_t smem = sizeof(float) * C3P_NCELL * a.Csrc * a.Nout;
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default too)
     C3P_CUDA(cudaFuncSetAttribute(k_small_gather_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
   long long grid = (long long)sc_sms() * per_sm;
@@ -235,12 +238,14 @@ static int launch_small_gc(SCArgs& a, const char* name, cudaStream_t stream) {
 }
 
 int launch_forward_small(const conv3p_geom_t* g, const PlanView& v, const float* input, const float* filter,
-                         int Cin, int Cout, float* output, cudaStream_t stream) {
+                         int Cin, int Cout, float* output, cudaStream_t stream, const RowIO& io) {
   SCArgs a{};
   a.src = input; a.filter = filter; a.out = output; a.cnt = v.count_table; a.begin = v.pair_begin;
   a.len = v.pair_len; a.rows = v.pair_row; a.weights = nullptr; a.sorted_xyzi = v.sorted_xyzi;
   a.total_points = (long long)g->B * g->N; a.capacity = g->pair_capacity; a.N = g->N;
   a.Cin = Cin; a.Cout = Cout; a.Csrc = Cin; a.Nout = Cout; a.transposed = 0;
+  a.src_stride = io.src_stride ? io.src_stride : Cin; a.out_stride = io.out_stride ? io.out_stride : Cout;
+  a.activation = io.activation;
   return launch_small_gc(a, "k_small_forward", stream);
 }
 
@@ -252,6 +257,7 @@ int launch_backward_input_small(const conv3p_geom_t* g, const PlanView& v, const
   a.len = v.pair_len; a.rows = v.bwd_row; a.weights = v.bwd_weight; a.sorted_xyzi = v.sorted_xyzi;
   a.total_points = (long long)g->B * g->N; a.capacity = g->pair_capacity; a.N = g->N;
   a.Cin = Cin; a.Cout = Cout; a.Csrc = Cout; a.Nout = Cin; a.transposed = 1;
+  a.src_stride = Cout; a.out_stride = Cin; a.activation = 0;
   return launch_small_gc(a, "k_small_backward_input", stream);
 }
 
@@ -275,7 +281,7 @@ int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, cons
   a.partial = static_cast<float*>(scratch);
   a.total_points = pts; a.capacity = g->pair_capacity; a.N = g->N; a.Cin = Cin; a.Cout = Cout;
   const size_t smem = sizeof(float) * (size_t)SC_WARPS * nW;
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default too)
     C3P_CUDA(cudaFuncSetAttribute(k_small_backward_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = smem > 100 * 1024 ? 1 : 2;
   int sms = sc_sms();

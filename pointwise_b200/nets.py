@@ -8,6 +8,10 @@ exercise plan sharing; they are not part of the hot path.
 * ``PointConvNetSeg``  -- scene_seg/pointcnn_scene_seg_acsd.py:32-71: four 9-channel layers (strides 1..4), concat,
   one 36->num_class layer at stride 1, every layer followed by SELU; softmax cross-entropy per point.
 
+Every Conv3p is followed by SELU in both networks; the layers call ``conv3p(..., activation="selu")``, which applies it
+in the kernel's epilogue, and ``features_fused`` (inference) additionally writes the four 9-channel
+outputs straight into the [B, N, 36] concat buffer and lets each layer read its predecessor's slice of it.
+
 A ``PlanCache`` builds one neighbour plan per (points, stride) and hands it to every layer that needs it and to
 the backward pass; the reference rebuilds its grid twice per layer per step (tf_conv3p_atrous.cpp:463, 629).
 """
@@ -19,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import NeighborPlan, conv3p, parse_stride, parse_voxel
+from .ops import NeighborPlan, conv3p, conv3p_forward, parse_stride, parse_voxel
 
 
 class PlanCache:
@@ -35,6 +39,22 @@ class PlanCache:
         if s not in self.plans:
             self.plans[s] = NeighborPlan(self.points, s, self.voxel)
         return self.plans[s]
+
+
+@torch.no_grad()
+def features_fused(plans: PlanCache, input_tensor: torch.Tensor, filters) -> torch.Tensor:
+    """The stack of 9-channel Conv3p+SELU layers at strides 1, 2, 3, ... (pointcnn2_acsd.py:48-69,
+    scene_seg/pointcnn_scene_seg_acsd.py:51-56) written straight into the concat buffer: layer i stores
+    selu(conv3p(.)) in channels [9i, 9i+9) and layer i+1 gathers from that slice -- no activation pass, no concat."""
+    B, N = input_tensor.shape[0], input_tensor.shape[1]
+    widths = [int(w.shape[4]) for w in filters]
+    concat = torch.empty((B, N, sum(widths)), dtype=torch.float32, device=input_tensor.device)
+    x, c0 = input_tensor, 0
+    for i, w in enumerate(filters):
+        out = concat[:, :, c0:c0 + widths[i]]
+        conv3p_forward(plans.get([i + 1] * 3), x, w, activation="selu", out=out)
+        x, c0 = out, c0 + widths[i]
+    return concat
 
 
 def _filter(cin: int, cout: int) -> nn.Parameter:
@@ -59,13 +79,19 @@ class PointConvNetCls(nn.Module):
         x, feats = input_tensor, []
         for i, w in enumerate(self.filters):                      # strides 1,2,3,4 -- :48-67
             stride = [i + 1] * 3
-            x = F.selu(conv3p(points_tensor, x, w, stride, [self.voxel], plan=plans.get(stride)))
+            x = conv3p(points_tensor, x, w, stride, [self.voxel], plan=plans.get(stride), activation="selu")
             feats.append(x)
         feat = torch.cat(feats, dim=2)                            # :69
         view = feat.reshape(feat.shape[0], -1)                    # :70
         fc1 = F.selu(self.fc1(view))                              # :71
         drop = F.alpha_dropout(fc1, p=0.5, training=is_training)  # selu.dropout_selu, :73
         return F.selu(self.fc2(drop))                             # :75
+
+    @torch.no_grad()
+    def infer(self, points_tensor: torch.Tensor, input_tensor: torch.Tensor) -> torch.Tensor:
+        """Inference with the concat-free layout (no dropout): same values as ``model(..., is_training=False)``."""
+        feat = features_fused(PlanCache(points_tensor, self.voxel), input_tensor, list(self.filters))
+        return F.selu(self.fc2(F.selu(self.fc1(feat.reshape(feat.shape[0], -1)))))
 
     forward = model
 
@@ -88,12 +114,20 @@ class PointConvNetSeg(nn.Module):
         x, feats = input_tensor, []
         for i in range(4):                                         # :51-54
             stride = [i + 1] * 3
-            x = F.selu(conv3p(points_tensor, x, self.filters[i], stride, [self.voxel], plan=plans.get(stride)))
+            x = conv3p(points_tensor, x, self.filters[i], stride, [self.voxel], plan=plans.get(stride),
+                       activation="selu")
             feats.append(x)
         concat = torch.cat(feats, dim=2)                           # :56
         # layer 5 reuses the stride-1 plan of layer 1
-        return F.selu(conv3p(points_tensor, concat, self.filters[4], [1, 1, 1], [self.voxel],
-                             plan=plans.get([1, 1, 1])))           # :57
+        return conv3p(points_tensor, concat, self.filters[4], [1, 1, 1], [self.voxel],
+                      plan=plans.get([1, 1, 1]), activation="selu")  # :57
+
+    @torch.no_grad()
+    def infer(self, points_tensor: torch.Tensor, input_tensor: torch.Tensor) -> torch.Tensor:
+        """Inference with the concat-free layout: same values as ``model`` without the SELU passes and the concat."""
+        plans = PlanCache(points_tensor, self.voxel)
+        concat = features_fused(plans, input_tensor, list(self.filters)[:4])
+        return conv3p_forward(plans.get([1, 1, 1]), concat, self.filters[4], activation="selu")
 
     forward = model
 

@@ -238,18 +238,67 @@ class NeighborPlan:
 # --------------------------------------------------------------------------------------------------
 # forward / backward on a plan
 # --------------------------------------------------------------------------------------------------
-def conv3p_forward(plan: NeighborPlan, input: torch.Tensor, kernel: torch.Tensor) -> torch.Tensor:
-    input = _check_cuda_f32(input, "input")
+ACTIVATIONS = {None: 0, "none": 0, "selu": 1}
+
+
+def _rows_view(t: torch.Tensor, name: str, B: int, N: int):
+    """-> (tensor, row stride in floats) for a [B,N,C] float32 CUDA tensor whose rows may sit inside a wider
+    row-major buffer (a channel slice ``buf[:, :, a:b]`` of a contiguous [B,N,W] tensor); anything else is made
+    contiguous."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"Conv3p: {name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"Conv3p: {name} must be a CUDA tensor (pointwise_b200 has no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"Conv3p: {name} must be float32 (got {t.dtype})")
+    if t.dim() == 3 and t.shape[0] == B and t.shape[1] == N and t.numel() > 0:
+        C = t.shape[2]
+        sb, sn, sc = t.stride()
+        if (sc == 1 or C == 1) and sn >= C and (B == 1 or sb == N * sn):
+            return t, int(sn)
+    t = t.contiguous()
+    return t, int(t.shape[-1]) if t.dim() else 0
+
+
+def conv3p_forward(plan: NeighborPlan, input: torch.Tensor, kernel: torch.Tensor,
+                   activation: Optional[str] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Conv3p forward on a built plan.  ``activation="selu"`` fuses the SELU the reference's networks apply to every
+    Conv3p output into the kernel's epilogue; ``input`` may be a channel slice of a wider [B,N,W] buffer and
+    ``out`` (optional) such a slice to write into -- the concat of the 9-channel layers then needs no copy
+    (scene_seg/pointcnn_scene_seg_acsd.py:35-36, :56)."""
+    if activation not in ACTIVATIONS:
+        raise ValueError(f"Conv3p: unknown activation {activation!r}")
     kernel = _check_cuda_f32(kernel, "kernel")
     Cin, Cout = int(kernel.shape[3]), int(kernel.shape[4])
-    out = torch.empty((plan.B, plan.N, Cout), dtype=torch.float32, device=plan.device)
+    input, in_stride = _rows_view(input, "input", plan.B, plan.N)
+    if out is None:
+        out = torch.empty((plan.B, plan.N, Cout), dtype=torch.float32, device=plan.device)
+        out_stride = Cout
+    else:
+        if tuple(out.shape) != (plan.B, plan.N, Cout):
+            raise ValueError("Conv3p: out must have shape [B, N, Cout]")
+        view, out_stride = _rows_view(out, "out", plan.B, plan.N)
+        if view.data_ptr() != out.data_ptr():
+            raise ValueError("Conv3p: out must be a channel slice of a contiguous [B, N, W] buffer")
     L = _lib.lib()
     nscratch = L.conv3p_scratch_bytes(plan.geom, Cin, Cout)
     scratch = torch.empty(nscratch, dtype=torch.uint8, device=plan.device)
     with torch.cuda.device(plan.device):
-        _lib.check(L.conv3p_forward_f32(plan.geom, _ptr(plan.buffer), _ptr(input), _ptr(kernel),
-                                        Cin, Cout, _ptr(out), _ptr(scratch), nscratch,
-                                        _stream_ptr(plan.device)))
+        _lib.check(L.conv3p_forward_ex_f32(plan.geom, _ptr(plan.buffer), _ptr(input), in_stride, _ptr(kernel),
+                                           Cin, Cout, _ptr(out), out_stride, ACTIVATIONS[activation],
+                                           _ptr(scratch), nscratch, _stream_ptr(plan.device)))
+    return out
+
+
+def selu_backward(y: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
+    """grad * selu'(x) from the activated value y = selu(x) (the backward of the fused epilogue) -> dense [B,N,C]."""
+    B, N, Cc = int(y.shape[0]), int(y.shape[1]), int(y.shape[2])
+    y, ys = _rows_view(y, "y", B, N)
+    grad, gs = _rows_view(grad, "grad", B, N)
+    out = torch.empty((B, N, Cc), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.lib().conv3p_selu_backward_f32(_ptr(y), ys, _ptr(grad), gs, _ptr(out), B * N, Cc,
+                                                      _stream_ptr(y.device)))
     return out
 
 
@@ -292,29 +341,39 @@ def conv3p_backward(plan: NeighborPlan, grad_output: torch.Tensor, input: torch.
 
 class _Conv3pFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, points, input, kernel, plan):
+    def forward(ctx, points, input, kernel, plan, activation=None):
         ctx.plan = plan
-        ctx.save_for_backward(input, kernel)
-        return conv3p_forward(plan, input, kernel)
+        ctx.activation = activation
+        out = conv3p_forward(plan, input, kernel, activation=activation)
+        if activation == "selu":
+            ctx.save_for_backward(input, kernel, out)
+        else:
+            ctx.save_for_backward(input, kernel)
+        return out
 
     @staticmethod
     def backward(ctx, grad_output):
-        input, kernel = ctx.saved_tensors
+        if ctx.activation == "selu":
+            input, kernel, out = ctx.saved_tensors
+            grad_output = selu_backward(out, grad_output)
+        else:
+            input, kernel = ctx.saved_tensors
         gi, gf = conv3p_backward(ctx.plan, grad_output, input, kernel,
                                  need_input_grad=ctx.needs_input_grad[1],
                                  need_filter_grad=ctx.needs_input_grad[2])
         # the reference returns [None, input_grad, filter_grad, None, None] (pointcnn2_acsd.py:31)
-        return None, gi, gf, None
+        return None, gi, gf, None, None
 
 
 def conv3p(points_tensor, input_tensor, kernel_tensor, stride, voxel_size,
-           plan: Optional[NeighborPlan] = None) -> torch.Tensor:
+           plan: Optional[NeighborPlan] = None, activation: Optional[str] = None) -> torch.Tensor:
     """Drop-in for the reference's ``conv3p`` (pointcnn2_acsd.py:12-13): same positional signature.
 
     points [B,N,3], input [B,N,Cin], kernel [3,3,3,Cin,Cout] (z,y,x,in,out), stride = 3 ints (x,y,z),
     voxel_size = 1 float; returns [B,N,Cout].  Differentiable w.r.t. input and kernel only
     (pointcnn2_acsd.py:31).  ``plan`` optionally reuses a NeighborPlan built for the same points,
-    stride and voxel size (e.g. across layers).
+    stride and voxel size (e.g. across layers).  ``activation="selu"`` returns ``selu(conv3p(...))`` with the
+    activation fused into the kernel's epilogue (and its derivative applied to the incoming gradient in backward).
     """
     points = _check_cuda_f32(points_tensor, "points")
     input = _check_cuda_f32(input_tensor, "input")
@@ -325,7 +384,9 @@ def conv3p(points_tensor, input_tensor, kernel_tensor, stride, voxel_size,
         plan = NeighborPlan(points, s, v)
     elif not plan.matches(points, s, v):
         raise ValueError("Conv3p: the supplied NeighborPlan was built for different points/stride/voxel_size")
-    return _Conv3pFunction.apply(points, input, kernel, plan)
+    if activation not in ACTIVATIONS:
+        raise ValueError(f"Conv3p: unknown activation {activation!r}")
+    return _Conv3pFunction.apply(points, input, kernel, plan, None if activation in (None, "none") else activation)
 
 
 def conv3p_grad(grad_from_next, points, input, filter, stride, voxel_size,

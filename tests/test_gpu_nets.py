@@ -52,7 +52,7 @@ def test_classification_net_trains():
         loss.backward()
         n_launch = launch_count()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
     assert losses[-1] < losses[0]
     assert n_launch > 0
@@ -64,3 +64,79 @@ def test_plan_cache_shares_plans():
     pc = PlanCache(pts, 0.1)
     a, b, c = pc.get([1, 1, 1]), pc.get(torch.tensor([1, 1, 1])), pc.get([2, 2, 2])
     assert a is b and a is not c
+
+
+# ---- SELU fused into the epilogue, concat-free layout ------------------------------------------
+@pytest.mark.parametrize("Cin,Cout,stride", [(9, 9, 1), (36, 13, 1), (64, 128, 1), (32, 64, 2), (40, 48, 1)])
+def test_fused_selu_epilogue_matches_selu_of_plain_output(Cin, Cout, stride):
+    """activation="selu" == selu(unfused output) on every forward engine (warp-per-point, tile, tensor core);
+    the unfused output itself is held to the oracle in test_gpu_parity.py."""
+    from pointwise_b200 import NeighborPlan, conv3p_forward
+    from pointwise_b200.synth import make_problem
+    pr = make_problem(3, 700, Cin, Cout, "room", seed=11)
+    plan = NeighborPlan(torch.from_numpy(pr["points"]).cuda(), (stride,) * 3, 0.1)
+    x, w = torch.from_numpy(pr["input"]).cuda(), torch.from_numpy(pr["filter"]).cuda()
+    plain = conv3p_forward(plan, x, w)
+    fused = conv3p_forward(plan, x, w, activation="selu")
+    want = selu_np(plain.cpu().numpy().astype(np.float64))
+    np.testing.assert_allclose(fused.cpu().numpy(), want, rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("Cin,Cout,W_in,W_out,c_in,c_out", [(9, 9, 36, 36, 9, 18), (64, 128, 96, 160, 32, 16),
+                                                            (9, 13, 11, 17, 1, 3)])
+def test_strided_rows_in_and_out(Cin, Cout, W_in, W_out, c_in, c_out):
+    """Input read from / output written into channel slices of wider buffers: same values as the dense call, and
+    nothing outside the output slice is touched.  (Third case: rows not 16-byte aligned -> fp32 engines.)"""
+    from pointwise_b200 import NeighborPlan, conv3p_forward
+    from pointwise_b200.synth import make_problem
+    B, N = 2, 600
+    pr = make_problem(B, N, Cin, Cout, "room", seed=12)
+    plan = NeighborPlan(torch.from_numpy(pr["points"]).cuda(), (1, 1, 1), 0.1)
+    x, w = torch.from_numpy(pr["input"]).cuda(), torch.from_numpy(pr["filter"]).cuda()
+    dense = conv3p_forward(plan, x, w, activation="selu")
+    wide_in = torch.full((B, N, W_in), float("nan"), device="cuda")
+    wide_in[:, :, c_in:c_in + Cin] = x
+    wide_out = torch.full((B, N, W_out), -7.0, device="cuda")
+    ret = conv3p_forward(plan, wide_in[:, :, c_in:c_in + Cin], w, activation="selu",
+                         out=wide_out[:, :, c_out:c_out + Cout])
+    assert ret.data_ptr() == wide_out[:, :, c_out:c_out + Cout].data_ptr()
+    assert torch.equal(wide_out[:, :, c_out:c_out + Cout], dense)
+    assert float((wide_out[:, :, :c_out] + 7.0).abs().max()) == 0.0
+    assert float((wide_out[:, :, c_out + Cout:] + 7.0).abs().max() if c_out + Cout < W_out else 0.0) == 0.0
+
+
+def test_fused_selu_gradients_match_autograd_of_unfused():
+    """conv3p(..., activation="selu") and F.selu(conv3p(...)) give the same output and the same gradients."""
+    import torch.nn.functional as F
+    from pointwise_b200 import conv3p
+    from pointwise_b200.synth import make_problem
+    for Cin, Cout in [(9, 9), (64, 128)]:
+        pr = make_problem(2, 800, Cin, Cout, "room", seed=13)
+        P = torch.from_numpy(pr["points"]).cuda()
+        g = torch.from_numpy(pr["grad_out"]).cuda()
+        res = []
+        for fused in (True, False):
+            x = torch.from_numpy(pr["input"]).cuda().requires_grad_()
+            w = torch.from_numpy(pr["filter"]).cuda().requires_grad_()
+            y = conv3p(P, x, w, [1, 1, 1], [0.1], activation="selu") if fused else F.selu(conv3p(P, x, w, [1, 1, 1], [0.1]))
+            y.backward(g)
+            res.append((y.detach(), x.grad, w.grad))
+        for a, b in zip(*res):
+            scale = float(b.abs().max())
+            assert float((a - b).abs().max()) <= 3e-6 * scale + 1e-7
+
+
+def test_concat_free_inference_matches_model():
+    """PointConvNetSeg.infer / PointConvNetCls.infer (layers write into the concat buffer, SELU in the epilogue)
+    reproduce model() (separate SELU, torch.cat)."""
+    from pointwise_b200.nets import PointConvNetCls, PointConvNetSeg
+    torch.manual_seed(3)
+    B, N = 2, 1024
+    pts = torch.from_numpy(make_points(B, N, "room", seed=4)).cuda()
+    feats = torch.from_numpy(np.random.default_rng(6).uniform(-1, 1, (B, N, 9)).astype(np.float32)).cuda()
+    seg = PointConvNetSeg(13, 9).cuda()
+    a, b = seg.model(pts, feats).detach(), seg.infer(pts, feats)
+    assert float((a - b).abs().max()) <= 1e-6 * float(a.abs().max()) + 1e-7
+    cls = PointConvNetCls(40, N, 3).cuda()
+    a, b = cls.model(pts, pts.clone(), is_training=False).detach(), cls.infer(pts, pts.clone())
+    assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-6
