@@ -148,6 +148,22 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
                         float* grad_input, float* grad_filter, void* scratch, size_t scratch_bytes,
                         conv3p_stream_t stream);
 
+/* ---- input pipeline on the GPU (reference: modelnet_provider.py:23-75, util.py:55-109) -------- */
+/* out[b,i,:] = float32(clip(sigma * noise[b,i,:], -clip, clip) + float32(data[b,i,:] @ R_y(angles[b]))) --
+ * rotate_point_cloud followed by jitter_point_cloud on [B,N,3] clouds.  The random draws are inputs (float64, as
+ * numpy produces them): one angle per cloud, one standard-normal sample per coordinate; either may be NULL to skip
+ * that stage.  Arithmetic in double, rounded to float32 once per stage like the provider's float32 arrays. */
+int conv3p_augment_rotate_jitter_f32(const float* data, const double* angles, const double* noise, double sigma,
+                                     double clip, int B, int N, float* out, conv3p_stream_t stream);
+
+/* sort_point_cloud_xyz / sort_point_cloud_xyz2: every cloud's rows ordered by x, then y, then z (the first three of
+ * K channels), ties by original position.  order[B,N] receives the source row of every output row; sorted_data
+ * [B,N,K] and sorted_attributes [B,N,M] (optional, may be NULL) the permuted rows. */
+size_t conv3p_xyz_sort_workspace_bytes(int B, int N);
+int conv3p_xyz_sort_f32(const float* data, int K, const float* attributes, int M, int B, int N, int* order,
+                        float* sorted_data, float* sorted_attributes, void* workspace, size_t workspace_bytes,
+                        conv3p_stream_t stream);
+
 /* ---- one-shot operator calls with the reference's Compute() shape ----------------------------- */
 /* workspace >= conv3p_op_workspace_bytes(); holds plan + scratch.  filter_dims = {fz,fy,fx}. */
 size_t conv3p_op_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout);

@@ -8,11 +8,10 @@
 // the exact predicate to a superset of candidates -- so dims are clamped to 1024 per axis (a 30-bit
 // key); clouds wider than 1023 voxels merely share their last cell.
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace c3p {
 
-constexpr int SORT_THREADS = 512;
-constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int MAX_DIM = 1024;
 
 __global__ void __launch_bounds__(SORT_THREADS)
@@ -96,64 +95,8 @@ k_cloud_sort(const float* __restrict__ points, int N, float voxel, float* __rest
   __syncthreads();
 
   // ---- stable LSD radix sort, 8 bits per pass -----------------------------------------------------
-  for (int shift = 0; shift < nbits; shift += 8) {
-    if (tid < 256) base[tid] = 0;
-    __syncthreads();
-    for (int i = tid; i < N; i += SORT_THREADS) atomicAdd(&base[(kin[i] >> shift) & 255u], 1u);
-    __syncthreads();
-    uint32_t h = 0, inc = 0;
-    if (tid < 256) {  // exclusive scan of the 256 digit counts
-      h = base[tid];
-      inc = h;
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t u = __shfl_up_sync(C3P_FULL_MASK, inc, o);
-        if (lane >= o) inc += u;
-      }
-      if (lane == 31) wsum[warp] = inc;
-    }
-    __syncthreads();
-    if (tid < 256) {
-      uint32_t off = 0;
-      for (int w = 0; w < warp; ++w) off += wsum[w];
-      base[tid] = off + inc - h;
-    }
-    __syncthreads();
-
-    for (int c0 = 0; c0 < N; c0 += SORT_THREADS) {
-      const int i = c0 + tid;
-      const bool valid = i < N;
-      uint32_t key = 0, idx = 0, d = 0xffffffffu;
-      if (valid) {
-        key = kin[i];
-        idx = iin[i];
-        d = (key >> shift) & 255u;
-      }
-      const unsigned peers = __match_any_sync(C3P_FULL_MASK, d);
-      const int rank = __popc(peers & lanemask_lt());
-      if (valid && rank == 0) wcount[warp][d] = (uint16_t)__popc(peers);
-      __syncthreads();
-      uint32_t run = 0;
-      if (tid < 256) {
-#pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
-          wpre[w][tid] = (uint16_t)run;
-          run += wcount[w][tid];
-        }
-      }
-      __syncthreads();
-      if (valid) {
-        uint32_t pos = base[d] + wpre[warp][d] + rank;
-        kout[pos] = key;
-        iout[pos] = idx;
-        if (rank == 0) wcount[warp][d] = 0;  // leave the table clean for the next chunk
-      }
-      __syncthreads();
-      if (tid < 256) base[tid] += run;
-    }
-    __syncthreads();
-    uint32_t* t0 = kin; kin = kout; kout = t0;
-    uint32_t* t1 = iin; iin = iout; iout = t1;
-  }
+  RadixTables tb{base, wsum, wcount, wpre};
+  radix_sort_pairs(kin, iin, kout, iout, N, 0, nbits, tb);
 
   // ---- emit sorted keys and (x, y, z, index) ------------------------------------------------------
   for (int s = tid; s < N; s += SORT_THREADS) {

@@ -10,7 +10,9 @@ import pytest
 from helpers import pair_sets
 from pointwise_b200.synth import make_problem
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
+GOLDEN = sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith("augment_"))
+AUGMENT = sorted(glob.glob(os.path.join(GOLDEN_DIR, "augment_*.npz")))
 V = 0.1
 
 
@@ -116,3 +118,23 @@ def test_asymmetric_pairs_exist_on_quantised_clouds(port):
         rhs = (gi.astype(np.float64) * pr["input"]).sum()
         close = abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
         assert close == expect_equal
+
+
+# ---- input pipeline checker (oracle/augment_oracle.py) against outputs of the reference's own functions ------------
+def test_augment_fixtures_present():
+    assert len(AUGMENT) == 4
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_augment_oracle_matches_reference_outputs(tag):
+    from oracle import augment_oracle as ao
+    d = np.load(os.path.join(GOLDEN_DIR, f"augment_rotate_jitter_{tag}.npz"))
+    assert np.array_equal(ao.rotate_jitter(d["data"], d["angles"], d["noise"]), d["out"])
+    d = np.load(os.path.join(GOLDEN_DIR, f"augment_sort_xyz_{tag}.npz"))
+    assert np.array_equal(ao.sort_xyz(d["data"]), d["sorted"])
+    sp, sa = ao.sort_xyz(d["points"], d["attributes"])
+    assert np.array_equal(sp, d["sorted_points"]) and np.array_equal(sa, d["sorted_attributes"])
+    # the sorted rows really are in (x, y, z) order
+    for k in range(sp.shape[0]):
+        keys = [tuple(r) for r in sp[k]]
+        assert keys == sorted(keys)
