@@ -364,18 +364,22 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
       }
       ++p_g;  // the END slot
       if (timed) { tk = clock64(); ph[1] += (unsigned)(tk - tl); }
-      // =========================== epilogue: TMEM -> registers -> global ==============================
+      // =========================== epilogue: TMEM -> registers -> shared -> global ======================
+      // tcgen05.ld hands every lane one accumulator ROW; stored from there, a warp store touches 32 different
+      // 128-byte lines with 16 bytes each (32 wavefronts per instruction -- measured 6 % of the kernel).  The
+      // 32 x 32 block is therefore transposed through a 4 KB tile of the (now idle) operand ring, so that eight
+      // lanes write one full 128-byte row segment and a store instruction covers four lines.
       mbar_wait(bar(G2B_ACC_FULL, 0), (uint32_t)(chunk & 1));
       tc_fence_after_sync();
       G2_PHASE(2);
+      const uint32_t tile = s_a + (uint32_t)warp * 4096u;
+      const float qnan = __int_as_float(0x7fc00000);
       for (int task = warp; task < 4 * T; task += G2_NPW) {
         const int t = task >> 2, sub = task & 3;
         bool any = false;
         for (int f = 0; f < C3P_NCELL; ++f) any |= ((active[f] >> t) & 1u) != 0;
-        const int pt = t * 128 + sub * 32 + lane;
-        int row = rowid[pt];
-        const bool poison = row < -1;
-        if (poison) row = -2 - row;
+        const int pt0 = t * 128 + sub * 32;
+        const bool poison = rowid[pt0 + lane] < -1;
         for (int c0_ = 0; c0_ < Nout; c0_ += 32) {
           float v[32];
           if (any) {
@@ -384,22 +388,28 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (row >= 0) {
-            float* o = a.out + (size_t)row * a.out_stride + c0_;
-            if (a.activation) {
+          if (a.activation) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_activation(v[j], a.activation);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (c0_ + j < Nout) {
-                float4 w4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (poison) w4 = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
-                                             __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
-                *reinterpret_cast<float4*>(o + j) = w4;
-              }
-            }
+            for (int j = 0; j < 32; ++j) v[j] = apply_activation(v[j], a.activation);
           }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 w4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (poison) w4 = make_float4(qnan, qnan, qnan, qnan);
+            sts128(tile + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), w4);
+          }
+          __syncwarp();
+          const int c = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            int row = rowid[pt0 + r];
+            if (row < -1) row = -2 - row;
+            const float4 w4 = lds128(tile + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
+            if (row >= 0 && c0_ + c * 4 < Nout)
+              *reinterpret_cast<float4*>(a.out + (size_t)row * a.out_stride + c0_ + c * 4) = w4;
+          }
+          __syncwarp();
         }
       }
       G2_PHASE(3);
