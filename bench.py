@@ -251,6 +251,7 @@ def gpu_arm(args):
     def step_device():
         plan = NeighborPlan(devt["points"], stride, VOXEL, check=False, capacity=capacity)
         y = conv3p_forward(plan, devt["input"], devt["filter"])
+        plan.prefetch_backward()         # what the autograd op does when a gradient is required
         gi, gf = conv3p_backward(plan, devt["grad_out"], devt["input"], devt["filter"])
         if world > 1:
             allreduce_grad_filter(gf)

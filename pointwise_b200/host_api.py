@@ -72,6 +72,7 @@ class HostConv3p:
             plan = NeighborPlan(s["points"], self.stride, self.voxel, capacity=self.capacity,
                                 check=self.capacity is None)
             out = conv3p_forward(plan, s["input"], s["filter"])
+            plan.prefetch_backward()
             gi, gf = conv3p_backward(plan, s["grad_out"], s["input"], s["filter"])
             if allreduce is not None:
                 allreduce(gf)

@@ -99,6 +99,16 @@ def _stream_ptr(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+_side_streams = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device)
+    return _side_streams[key]
+
+
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -166,6 +176,10 @@ class NeighborPlan:
         lay = _lib.PlanLayout()
         _lib.check(L.conv3p_plan_layout(self.geom, lay))
         self.layout = lay
+        # the forward lists are complete at this point of the stream: a later prefetch_backward() starts from here
+        self._searched = torch.cuda.Event()
+        self._searched.record(torch.cuda.current_stream(self.device))
+        self._bwd_ready = None
 
     # ---- stats / views -------------------------------------------------------------------------
     def read_stats(self):
@@ -221,7 +235,28 @@ class NeighborPlan:
         return self._view(self.layout.sorted_key, self.B * self.N, torch.int32).view(self.B, self.N)
 
     # ---- backward lists ----------------------------------------------------------------------------
+    def prefetch_backward(self) -> "NeighborPlan":
+        """Builds the backward lists on a side stream, ordered after the neighbour search only -- called once the
+        forward kernels are enqueued, the list kernel fills whatever the persistent forward CTAs leave free instead
+        of sitting between forward and backward on the main stream.  ensure_backward() joins it."""
+        if self.has_backward or self._bwd_ready is not None or self.B * self.N == 0:
+            return self
+        side = _side_stream(self.device)
+        side.wait_event(self._searched)
+        with torch.cuda.device(self.device), torch.cuda.stream(side):
+            _lib.check(_lib.lib().conv3p_plan_build_backward(
+                self.geom, _ptr(self.points), _ptr(self.buffer), self.buffer.numel(), C.c_void_p(side.cuda_stream)))
+            self._bwd_ready = torch.cuda.Event()
+            self._bwd_ready.record(side)
+        self.buffer.record_stream(side)
+        self.points.record_stream(side)
+        return self
+
     def ensure_backward(self) -> "NeighborPlan":
+        if self._bwd_ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._bwd_ready)
+            self._bwd_ready = None
+            self.has_backward = True
         if not self.has_backward:
             with torch.cuda.device(self.device):
                 _lib.check(_lib.lib().conv3p_plan_build_backward(
@@ -345,6 +380,8 @@ class _Conv3pFunction(torch.autograd.Function):
         ctx.plan = plan
         ctx.activation = activation
         out = conv3p_forward(plan, input, kernel, activation=activation)
+        if any(ctx.needs_input_grad):
+            plan.prefetch_backward()     # overlaps the rest of the forward pass
         if activation == "selu":
             ctx.save_for_backward(input, kernel, out)
         else:
