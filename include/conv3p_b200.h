@@ -167,6 +167,9 @@ int conv3p_xyz_sort_f32(const float* data, int K, const float* attributes, int M
 /* ---- one-shot operator calls with the reference's Compute() shape ----------------------------- */
 /* workspace >= conv3p_op_workspace_bytes(); holds plan + scratch.  filter_dims = {fz,fy,fx}. */
 size_t conv3p_op_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout);
+/* >= conv3p_op_workspace_bytes: with this much workspace conv3p_op_backward_f32 (and conv3p_host_backward_f32 for
+ * its device part) shares one gather between the two gradients, see conv3p_backward_scratch_bytes. */
+size_t conv3p_op_backward_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout);
 
 int conv3p_op_forward_f32(const float* points, const float* input, const float* filter,
                           const int filter_dims[3], const int stride_xyz[3], float voxel_size, int B,

@@ -424,6 +424,12 @@ size_t conv3p_op_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
   return p + conv3p_scratch_bytes(geom, Cin, Cout);
 }
 
+size_t conv3p_op_backward_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
+  size_t p = conv3p_plan_bytes(geom);
+  if (!p) return 0;
+  return p + conv3p_backward_scratch_bytes(geom, Cin, Cout);
+}
+
 static int check_filter_dims(const int filter_dims[3]) {
   if (!filter_dims) return CONV3P_ERR_INVALID_ARGUMENT;
   if (filter_dims[0] != 3 || filter_dims[1] != 3 || filter_dims[2] != 3) return CONV3P_ERR_UNSUPPORTED;

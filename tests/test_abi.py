@@ -50,6 +50,11 @@ def test_sizes_and_layout(L):
     assert lay.pair_begin - lay.count_table >= 16 * 4096 * 27 * 4
     assert L.conv3p_op_workspace_bytes(g, 64, 128) >= lay.total_bytes + 27 * 64 * 128 * 4
     assert L.conv3p_host_workspace_bytes(g, 64, 128) > L.conv3p_op_workspace_bytes(g, 64, 128)
+    # the G store (27 * Cout floats per point) only where both gradient kernels are the tensor-core ones
+    extra = L.conv3p_backward_scratch_bytes(g, 64, 128) - L.conv3p_scratch_bytes(g, 64, 128)
+    assert extra >= 16 * 4096 * 27 * 128 * 4
+    assert L.conv3p_op_backward_workspace_bytes(g, 64, 128) - L.conv3p_op_workspace_bytes(g, 64, 128) == extra
+    assert L.conv3p_backward_scratch_bytes(g, 9, 9) == L.conv3p_scratch_bytes(g, 9, 9)
     g0 = _lib.make_geom(0, 0, (1, 1, 1), 0.1, 0)
     assert L.conv3p_plan_bytes(g0) > 0
 

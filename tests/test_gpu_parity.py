@@ -350,6 +350,37 @@ def test_c_abi_one_shot_and_host_calls(port):
     assert_close_scaled(Y.cpu().numpy(), o64, oabs, RTOL, ATOL, "one-shot forward")
 
 
+def test_c_abi_one_shot_backward_with_and_without_shared_gather(port):
+    """conv3p_op_backward_f32 at a tensor-core shape: the minimum workspace (each gradient kernel gathers) and the
+    larger one of conv3p_op_backward_workspace_bytes (one gather, G store) give the same bits, both within tolerance
+    of the oracle."""
+    import ctypes as C
+    from pointwise_b200 import _lib
+    L = _lib.lib()
+    B, N, Cin, Cout, stride = 2, 900, 64, 128, (1, 1, 1)
+    pr = make_problem(B, N, Cin, Cout, "room", seed=18)
+    cap = 96 * B * N
+    g = _lib.make_geom(B, N, stride, V, cap)
+    i3 = (C.c_int * 3)
+    P, X, W, G = dev(pr["points"]), dev(pr["input"]), dev(pr["filter"]), dev(pr["grad_out"])
+    res = []
+    small, big = L.conv3p_op_workspace_bytes(g, Cin, Cout), L.conv3p_op_backward_workspace_bytes(g, Cin, Cout)
+    assert big > small
+    for nbytes in (small, big):
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        gi = torch.full((B, N, Cin), float("nan"), device="cuda")
+        gf = torch.full((3, 3, 3, Cin, Cout), float("nan"), device="cuda")
+        _lib.check(L.conv3p_op_backward_f32(G.data_ptr(), P.data_ptr(), X.data_ptr(), W.data_ptr(), i3(3, 3, 3),
+                                            i3(*stride), V, B, N, Cin, Cout, cap, gi.data_ptr(), gf.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), None))
+        torch.cuda.synchronize()
+        res.append((gi.cpu().numpy(), gf.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    r = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
+    assert_close_scaled(res[1][0], r[2], r[3], RTOL, ATOL, "one-shot grad_input")
+    assert_close_scaled(res[1][1], r[4], r[5], RTOL, ATOL, "one-shot grad_filter")
+
+
 @pytest.mark.parametrize("Cin,Cout", [(64, 128), (32, 64), (64, 64), (32, 128), (128, 32), (96, 48), (128, 128)])
 def test_tensor_core_engine_matches_oracle_and_simt(port, Cin, Cout):
     """The tcgen05 3xTF32 engine and the fp32 SIMT engine both sit inside the same tolerance
