@@ -314,7 +314,8 @@ def gpu_arm(args):
     # forward + backward (+ the all-reduce) and copies output / grad_input / grad_filter back to pinned host
     # memory; copies of neighbouring steps overlap the kernels (three streams, three staging slots).
     from pointwise_b200.host_api import HostConv3p
-    pipe = HostConv3p(hi - lo, N, Cin, Cout, stride, VOXEL, device=device, capacity=capacity)
+    pipe = HostConv3p(hi - lo, N, Cin, Cout, stride, VOXEL, device=device, capacity=capacity,
+                      depth=int(os.environ.get("CONV3P_HOST_DEPTH", "3")))
     ar = allreduce_grad_filter if world > 1 else None
 
     def run_e2e(steps):
