@@ -207,7 +207,9 @@ int conv3p_abi_version(void);
 long long conv3p_launch_count(int reset);
 /* Selects the contraction engine: 0 = auto, 1 = fp32 SIMT only (tile engine or warp-per-point engine by
  * channel count), 2 = tensor cores (3xTF32) where supported, 3 = generic fp32 tile engine only.  Values
- * >= 64 carry profiling/ablation bits (tools/engine_timing.py).  Returns the previous value.  Process-wide. */
+ * >= 64 carry profiling/ablation bits for A/B timing (tools/engine_timing.py, tools/ab_backward.py): 32|64 phase
+ * timers of the gather+MMA kernel, 128 first-generation tensor-core kernels, 256 no G store shared between the two
+ * gradient kernels.  Returns the previous value.  Process-wide. */
 int conv3p_set_engine(int engine);
 
 /* Per-kernel timing for benchmarks: while enabled, every kernel launch is bracketed by CUDA events
