@@ -62,6 +62,8 @@ struct G2Args {
 // cycles summed over CTAs (warp 0, lane 0): prologue | producer loop | wait for the last MMA | epilogue |
 // in the loop: item fetch | first gather | wait for a free ring stage | stores + second repetition + arrive
 __device__ unsigned long long g2_phase_cycles[8];
+// TIMED build: sum and max over CTAs of a CTA's total cycles (how uneven the dynamic schedule ends)
+__device__ unsigned long long g2_cta_cycles[2];
 
 // ---- pre-pass: compacted work-item lists per (sub-tile, cell) group ---------------------------------------------
 // One CTA per sub-tile of ROWS voxel-sorted points, one thread per row.  Within a group the rows are ranked by
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool timed = TIMED && tid == 0;
   long long tk = timed ? clock64() : 0;
+  const long long t_begin = tk;
   unsigned ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define G2_PHASE(i) do { if (TIMED && timed) { const long long t_ = clock64(); ph[i] += (unsigned)(t_ - tk); tk = t_; } } while (0)
 
@@ -530,8 +533,12 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
     __syncthreads();
     tc_fence_after_sync();
   }
-  if (TIMED && timed)
+  if (TIMED && timed) {
     for (int i = 0; i < 8; ++i) atomicAdd(&g2_phase_cycles[i], (unsigned long long)ph[i]);
+    const unsigned long long total = (unsigned long long)(clock64() - t_begin);
+    atomicAdd(&g2_cta_cycles[0], total);
+    atomicMax(&g2_cta_cycles[1], total);
+  }
   if (warp == G2_NPW + 1) tmem_dealloc(tmem, 512);
 }
 
@@ -668,6 +675,13 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
 }  // namespace c3p
 
 // profiling helper (tools/engine_timing.py): read and clear the phase timers of k_gather_mma2
+extern "C" int conv3p_debug_cta_cycles(unsigned long long* host2) {
+  unsigned long long zero[2] = {0, 0};
+  if (cudaMemcpyFromSymbol(host2, c3p::g2_cta_cycles, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;
+  if (cudaMemcpyToSymbol(c3p::g2_cta_cycles, zero, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;
+  return CONV3P_OK;
+}
+
 extern "C" int conv3p_debug_phase_cycles(unsigned long long* host8) {
   unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cudaMemcpyFromSymbol(host8, c3p::g2_phase_cycles, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;

@@ -28,11 +28,15 @@ for label, fn in [("forward", lambda: conv3p_forward(plan, pr["input"], pr["filt
                   ("backward", lambda: conv3p_backward(plan, pr["grad_out"], pr["input"], pr["filter"]))]:
     L.conv3p_set_engine(64 + 32)
     L.conv3p_debug_phase_cycles(buf)
+    cta = (C.c_ulonglong * 2)()
+    L.conv3p_debug_cta_cycles(cta)
     fn(); torch.cuda.synchronize()
     L.conv3p_debug_phase_cycles(buf)
+    L.conv3p_debug_cta_cycles(cta)
     L.conv3p_set_engine(0)
     tiles = min(148, (B * N + 127) // 128)
     v = [x / tiles for x in buf]
+    print(f"{label}: CTA total cycles mean {cta[0] / tiles:.0f}, max {cta[1]} (the launch ends with the slowest CTA)")
     print(f"{label}: k_gather_mma2 cycles per CTA (thread 0): prologue {v[0]:.0f} | producer loop {v[1]:.0f} | "
           f"wait last MMA {v[2]:.0f} | epilogue {v[3]:.0f} || in loop: item fetch {v[4]:.0f} | gather 0 {v[5]:.0f} | "
           f"ring wait {v[6]:.0f} | stores+rep 1+arrive {v[7]:.0f}")
