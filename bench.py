@@ -38,6 +38,7 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # name: (clouds per GPU, N, Cin, Cout, stride, distribution)
     "headline": (64, 4096, 64, 128, (1, 1, 1), "room"),
+    "headline_b16": (16, 4096, 64, 128, (1, 1, 1), "room"),   # BASELINE configs[4]: 128 clouds over 8 GPUs
     "s3dis_l1": (16, 4096, 9, 9, (1, 1, 1), "room"),
     "s3dis_l5": (16, 4096, 36, 13, (1, 1, 1), "room"),
     "modelnet_l2": (32, 1024, 9, 9, (2, 2, 2), "sphere"),
