@@ -11,6 +11,7 @@
 //                          copies and then the CTA partials are reduced in a fixed order
 //                          (tf_conv3p_atrous.cpp:694-716).  Used when 8 copies fit in shared memory.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace c3p {
 
@@ -109,6 +110,157 @@ __global__ void __launch_bounds__(SC_THREADS) k_small_gather_contract(const SCAr
   }
 }
 
+// Second version of the same operator for Csrc, Nout <= 16 -- the shapes of every 9-channel layer of the two
+// reference networks.  The first version walks a point's list cell by cell with lanes = channels (9 of 32 lanes
+// busy) and two dependent loads (id, row) per pair of members: ~22 exposed L2 round trips per point.  Here
+//   * lanes = (member slot, channel): G = 32 / Csrc slots walk the point's WHOLE list (all cells, it is grouped by
+//     ascending cell) in strides of G, four members in flight per slot; the cell of a member is found by a pointer
+//     that only moves forward; a slot's sum for a cell is written once to the slot's own copy A_g[cell][channel]
+//     in shared memory (no atomics, fixed order of additions);
+//   * the contraction runs over the non-empty cells only with lanes = (k group, output): KG = 32 / Nout groups share
+//     the (cell, k) pairs and are summed by shuffles in a fixed order.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// Lists of one point and the rows they gather (forward lists + input, or backward lists + grad_out).
+struct SC2Lists {
+  const float* src;
+  const int* cnt;
+  const long long* begin;
+  const int* len;
+  const int* rows;
+  const float* weights;    // nullptr: per-cell mean
+  long long src_stride, capacity;
+};
+
+// Phase 1 of the second-version kernels, by one warp for the point in `row`: A[f][ch] = sum over the members of
+// cell f of w * src[member][ch] (w = 1 / members, or the list's weights), in copy 0 of the warp's A area.
+// Returns the mask of non-empty cells; `ok` = the point's list is complete.
+__device__ __forceinline__ unsigned sc2_aggregate(const SC2Lists& p, int row, int lane, int Csrc, int G, uint32_t s_A,
+                                                  uint32_t s_pre, uint32_t s_inv, bool& ok) {
+  const int cell_words = C3P_NCELL * Csrc;
+  const int g = lane / Csrc, ch = lane - g * Csrc;
+  const long long bg = p.begin[row];
+  ok = bg + p.len[row] <= p.capacity;
+  const int mine = (ok && lane < C3P_NCELL) ? __ldg(p.cnt + (size_t)row * C3P_NCELL + lane) : 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(C3P_FULL_MASK, incl, o);
+    if (lane >= o) incl += u;
+  }
+  const int K = __shfl_sync(C3P_FULL_MASK, incl, 31);
+  const unsigned cells = __ballot_sync(C3P_FULL_MASK, mine > 0);
+  __syncwarp();
+  if (lane < C3P_NCELL) {
+    sts_f32(s_pre + 4u * lane, __int_as_float(incl - mine));
+    sts_f32(s_inv + 4u * lane, mine > 0 ? __fdiv_rn(1.f, (float)mine) : 0.f);
+  }
+  if (lane == 31) sts_f32(s_pre + 4u * C3P_NCELL, __int_as_float(K));
+  for (int e = lane; e < G * cell_words; e += 32) sts_f32(s_A + 4u * e, 0.f);
+  __syncwarp();
+  if (g < G) {
+    const uint32_t Ag = s_A + 4u * (uint32_t)(g * cell_words + ch);
+    const int* rlist = p.rows + bg;
+    const float* wlist = p.weights ? p.weights + bg : nullptr;
+    int cf = 0;                                        // cell of the member being accumulated
+    int next_start = __float_as_int(lds_f32(s_pre + 4u));   // pre[cf + 1]
+    float wc = lds_f32(s_inv);                         // 1 / members of cell cf
+    float acc = 0.f;
+    for (int e0 = g; e0 < K; e0 += 4 * G) {
+      int j[4];
+      float w[4], x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * G;
+        j[u] = e < K ? __ldg(rlist + e) : 0;
+        w[u] = (wlist && e < K) ? __ldg(wlist + e) : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = (e0 + u * G < K) ? __ldg(p.src + (size_t)j[u] * p.src_stride + ch) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * G;
+        if (e < K) {
+          if (e >= next_start) {                       // the member starts a later cell: close the current one
+            sts_f32(Ag + 4u * (uint32_t)(cf * Csrc), acc);
+            acc = 0.f;
+            do {
+              ++cf;
+              next_start = __float_as_int(lds_f32(s_pre + 4u * (uint32_t)(cf + 1)));
+            } while (e >= next_start);
+            wc = lds_f32(s_inv + 4u * (uint32_t)cf);
+          }
+          acc = fmaf(wlist ? w[u] : wc, x[u], acc);
+        }
+      }
+    }
+    if (g < K) sts_f32(Ag + 4u * (uint32_t)(cf * Csrc), acc);
+  }
+  __syncwarp();
+  // fold the G copies into copy 0, fixed order
+  for (int e = lane; e < cell_words; e += 32) {
+    float v = lds_f32(s_A + 4u * e);
+    for (int gg = 1; gg < G; ++gg) v += lds_f32(s_A + 4u * (uint32_t)(gg * cell_words + e));
+    sts_f32(s_A + 4u * e, v);
+  }
+  __syncwarp();
+  return cells;
+}
+
+constexpr int SC2_WARP_WORDS = C3P_NCELL * 32 + 64;   // per warp: A copies (<= 27 * 32 floats) | cell starts | 1 / members
+
+__global__ void __launch_bounds__(SC_THREADS) k_small_gather_contract2(const SCArgs a) {
+  extern __shared__ float sc2[];
+  const int Csrc = a.Csrc, Nout = a.Nout;
+  const int nWf = C3P_NCELL * Csrc * Nout;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = 32 / Csrc, KG = 32 / Nout;
+  // shared-window addresses, converted once (tc_common.cuh): filter | per warp: A copies, cell starts, 1 / members
+  const uint32_t s_w = tc::smem_u32_once(sc2);                                   // [27][Csrc][Nout]
+  const uint32_t s_A = s_w + 4u * (uint32_t)(((nWf + 3) & ~3) + warp * SC2_WARP_WORDS);   // [G][27][Csrc]
+  const uint32_t s_pre = s_A + 4u * (C3P_NCELL * 32);                            // [28] ints, pre[27] = K
+  const uint32_t s_inv = s_pre + 4u * 32;                                        // [27]
+  for (int e = threadIdx.x; e < nWf; e += SC_THREADS) {
+    const int n = e % Nout, k = (e / Nout) % Csrc, f = e / (Nout * Csrc);
+    sc2[e] = a.transposed ? a.filter[((size_t)f * a.Cin + n) * a.Cout + k]
+                          : a.filter[((size_t)f * a.Cin + k) * a.Cout + n];
+  }
+  __syncthreads();
+  const int kg = lane / Nout, nn = lane - kg * Nout;
+  const bool out_on = kg < KG;
+  SC2Lists L;
+  L.src = a.src; L.cnt = a.cnt; L.begin = a.begin; L.len = a.len; L.rows = a.rows; L.weights = a.weights;
+  L.src_stride = a.src_stride; L.capacity = a.capacity;
+  const long long stride = (long long)gridDim.x * SC_WARPS;
+  for (long long s = (long long)blockIdx.x * SC_WARPS + warp; s < a.total_points; s += stride) {
+    const int b = (int)(s / a.N);
+    const int row = b * a.N + __float_as_int(a.sorted_xyzi[s].w);
+    bool ok;
+    const unsigned cells = sc2_aggregate(L, row, lane, Csrc, G, s_A, s_pre, s_inv, ok);
+    // ---- phase 2: out[n] = sum over non-empty cells f, channels k of A[f][k] * W_f[k][n]; lanes = (k group, n) -------
+    float o = 0.f;
+    if (out_on) {
+      for (unsigned todo = cells; todo; todo &= todo - 1) {
+        const int f = __ffs(todo) - 1;
+        const uint32_t af = s_A + 4u * (uint32_t)(f * Csrc), wf = s_w + 4u * (uint32_t)(f * Csrc * Nout + nn);
+        for (int k = kg; k < Csrc; k += KG) o = fmaf(lds_f32(af + 4u * k), lds_f32(wf + 4u * (uint32_t)(k * Nout)), o);
+      }
+    }
+    // sum the KG partial sums in a fixed order (lanes nn, nn + Nout, nn + 2 Nout, ...)
+    float total = 0.f;
+    for (int q = 0; q < KG; ++q) total += __shfl_sync(C3P_FULL_MASK, o, (nn + q * Nout) & 31);
+    const float nanv = __int_as_float(0x7fc00000);
+    if (lane < Nout) a.out[(size_t)row * a.out_stride + lane] = ok ? apply_activation(total, a.activation) : nanv;
+  }
+}
+
 struct SFArgs {
   const float* grad_out;
   const float* input;
@@ -196,6 +348,55 @@ __global__ void __launch_bounds__(SC_THREADS) k_small_backward_filter(const SFAr
   }
 }
 
+// Second version of the weight gradient for Cin, Cout <= 16: the aggregate G_f[j, :] of every non-empty cell comes from
+// sc2_aggregate (whole list in flight, see above), then lanes = (k, c) pairs add the rank-1 update
+// x[j, k] * G_f[j, c] into the warp's private copy of grad_filter (plain read-modify-write, fixed order).
+__global__ void __launch_bounds__(SC_THREADS) k_small_backward_filter2(const SFArgs a) {
+  extern __shared__ float sf2[];   // [warps][27][Cin][Cout] private copies | per warp: A copies, cell starts, 1 / members
+  const int Cin = a.Cin, Cout = a.Cout;
+  const int nW = C3P_NCELL * Cin * Cout;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = 32 / Cout;
+  for (int e = threadIdx.x; e < SC_WARPS * nW; e += SC_THREADS) sf2[e] = 0.f;
+  __syncthreads();
+  const uint32_t s_all = tc::smem_u32_once(sf2);
+  const uint32_t s_gw = s_all + 4u * (uint32_t)(warp * nW);
+  const uint32_t s_A = s_all + 4u * (uint32_t)(((SC_WARPS * nW + 3) & ~3) + warp * SC2_WARP_WORDS);
+  const uint32_t s_pre = s_A + 4u * (C3P_NCELL * 32), s_inv = s_pre + 4u * 32;
+  SC2Lists L;
+  L.src = a.grad_out; L.cnt = a.cnt; L.begin = a.begin; L.len = a.len; L.rows = a.rows; L.weights = a.weights;
+  L.src_stride = Cout; L.capacity = a.capacity;
+  const int pairs = Cin * Cout;
+  const long long stride = (long long)gridDim.x * SC_WARPS;
+  for (long long s = (long long)blockIdx.x * SC_WARPS + warp; s < a.total_points; s += stride) {
+    const int b = (int)(s / a.N);
+    const int row = b * a.N + __float_as_int(a.sorted_xyzi[s].w);
+    const float x = lane < Cin ? __ldg(a.input + (size_t)row * Cin + lane) : 0.f;
+    bool ok;
+    const unsigned cells = sc2_aggregate(L, row, lane, Cout, G, s_A, s_pre, s_inv, ok);
+    if (!ok) continue;   // (an incomplete list has no cells: the mask is empty anyway)
+    for (int p0 = 0; p0 < pairs; p0 += 32) {
+      const int p = p0 + lane;
+      const int k = p / Cout, c = p - k * Cout;
+      const float xk = __shfl_sync(C3P_FULL_MASK, x, k & 31);
+      if (p < pairs) {
+        for (unsigned todo = cells; todo; todo &= todo - 1) {
+          const int f = __ffs(todo) - 1;
+          const uint32_t at = s_gw + 4u * (uint32_t)(f * pairs + p);
+          sts_f32(at, fmaf(xk, lds_f32(s_A + 4u * (uint32_t)(f * Cout + c)), lds_f32(at)));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* dst = a.partial + (size_t)blockIdx.x * nW;
+  for (int e = threadIdx.x; e < nW; e += SC_THREADS) {
+    float sum = 0.f;
+    for (int c = 0; c < SC_WARPS; ++c) sum += sf2[(size_t)c * nW + e];  // fixed order over the warps
+    dst[e] = sum;
+  }
+}
+
 __global__ void k_small_reduce(const float* __restrict__ partial, int S, int nW, float* __restrict__ out) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nW) return;
@@ -222,6 +423,21 @@ bool small_backward_filter_supported(int Cin, int Cout) {
 
 static int launch_small_gc(SCArgs& a, const char* name, cudaStream_t stream) {
   if (a.total_points == 0) return CONV3P_OK;
+  if (a.Csrc <= 16 && a.Nout <= 16 && !(engine() & 1024)) {   // engine bit 1024: first version (A/B timing)
+    const size_t smem2 = sizeof(float) * (((size_t)C3P_NCELL * a.Csrc * a.Nout + 3) / 4 * 4 +
+                                          (size_t)SC_WARPS * SC2_WARP_WORDS);
+    if (smem2 > 40 * 1024)
+      C3P_CUDA(cudaFuncSetAttribute(k_small_gather_contract2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    long long grid2 = (long long)sc_sms() * 4;
+    const long long need2 = (a.total_points + SC_WARPS - 1) / SC_WARPS;
+    if (grid2 > need2) grid2 = need2;
+    {
+      LaunchTimer timer_(name, stream);
+      k_small_gather_contract2<<<(unsigned)grid2, SC_THREADS, smem2, stream>>>(a);
+    }
+    C3P_LAUNCH_CHECK(name);
+    return CONV3P_OK;
+  }
   const size_t smem = sizeof(float) * C3P_NCELL * a.Csrc * a.Nout;
   if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default too)
     C3P_CUDA(cudaFuncSetAttribute(k_small_gather_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -280,9 +496,15 @@ int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, cons
   a.rows = v.bwd_row; a.weights = v.bwd_weight; a.sorted_xyzi = v.sorted_xyzi;
   a.partial = static_cast<float*>(scratch);
   a.total_points = pts; a.capacity = g->pair_capacity; a.N = g->N; a.Cin = Cin; a.Cout = Cout;
-  const size_t smem = sizeof(float) * (size_t)SC_WARPS * nW;
-  if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default too)
-    C3P_CUDA(cudaFuncSetAttribute(k_small_backward_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool v2 = Cin <= 16 && Cout <= 16 && !(engine() & 1024);   // engine bit 1024: first version (A/B timing)
+  const size_t smem = v2 ? sizeof(float) * (((size_t)SC_WARPS * nW + 3) / 4 * 4 + (size_t)SC_WARPS * SC2_WARP_WORDS)
+                         : sizeof(float) * (size_t)SC_WARPS * nW;
+  if (smem > 40 * 1024) {  // (static shared memory counts against the 48 KB default too)
+    if (v2)
+      C3P_CUDA(cudaFuncSetAttribute(k_small_backward_filter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      C3P_CUDA(cudaFuncSetAttribute(k_small_backward_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   const int per_sm = smem > 100 * 1024 ? 1 : 2;
   int sms = sc_sms();
   if (sms > 256) sms = 256;
@@ -291,7 +513,10 @@ int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, cons
   if (grid > need) grid = need;
   {
     LaunchTimer timer_("k_small_backward_filter", stream);
-    k_small_backward_filter<<<(unsigned)grid, SC_THREADS, smem, stream>>>(a);
+    if (v2)
+      k_small_backward_filter2<<<(unsigned)grid, SC_THREADS, smem, stream>>>(a);
+    else
+      k_small_backward_filter<<<(unsigned)grid, SC_THREADS, smem, stream>>>(a);
   }
   C3P_LAUNCH_CHECK("k_small_backward_filter");
   {
