@@ -328,7 +328,7 @@ def gpu_arm(args):
         for t in tickets[-(pipe.depth - 1):]:
             pipe.fetch(t)
 
-    run_e2e(3)
+    run_e2e(max(8, args.warmup))      # the first steps of a fresh process also fault in the pinned staging buffers
     e2e_steps = max(4, args.steps)
     barrier()
     t0 = time.perf_counter()

@@ -99,6 +99,8 @@ def _stream_ptr(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+# CONV3P_PREFETCH_BACKWARD=0 keeps the backward lists on the caller's stream (A/B timing)
+PREFETCH_BACKWARD = os.environ.get("CONV3P_PREFETCH_BACKWARD", "1") != "0"
 _side_streams = {}
 
 
@@ -239,7 +241,7 @@ class NeighborPlan:
         """Builds the backward lists on a side stream, ordered after the neighbour search only -- called once the
         forward kernels are enqueued, the list kernel fills whatever the persistent forward CTAs leave free instead
         of sitting between forward and backward on the main stream.  ensure_backward() joins it."""
-        if self.has_backward or self._bwd_ready is not None or self.B * self.N == 0:
+        if self.has_backward or self._bwd_ready is not None or self.B * self.N == 0 or not PREFETCH_BACKWARD:
             return self
         side = _side_stream(self.device)
         side.wait_event(self._searched)
