@@ -278,6 +278,19 @@ class NeighborPlan:
 ACTIVATIONS = {None: 0, "none": 0, "selu": 1}
 
 
+def row_stride_of(shape, strides, B: int, N: int) -> Optional[int]:
+    """Row stride (in elements) of a [B,N,C] tensor whose rows sit at a uniform distance inside a wider row-major
+    buffer -- a channel slice ``buf[:, :, a:b]`` of a contiguous [B,N,W] tensor -- or None when the layout is anything
+    else (the caller then makes it contiguous).  Pure function of shape and strides: tested on the CPU."""
+    if len(shape) != 3 or shape[0] != B or shape[1] != N or B * N * shape[2] == 0:
+        return None
+    C = shape[2]
+    sb, sn, sc = strides
+    if (sc == 1 or C == 1) and sn >= C and (B == 1 or sb == N * sn):
+        return int(sn)
+    return None
+
+
 def _rows_view(t: torch.Tensor, name: str, B: int, N: int):
     """-> (tensor, row stride in floats) for a [B,N,C] float32 CUDA tensor whose rows may sit inside a wider
     row-major buffer (a channel slice ``buf[:, :, a:b]`` of a contiguous [B,N,W] tensor); anything else is made
@@ -288,11 +301,10 @@ def _rows_view(t: torch.Tensor, name: str, B: int, N: int):
         raise RuntimeError(f"Conv3p: {name} must be a CUDA tensor (pointwise_b200 has no CPU fallback)")
     if t.dtype != torch.float32:
         raise TypeError(f"Conv3p: {name} must be float32 (got {t.dtype})")
-    if t.dim() == 3 and t.shape[0] == B and t.shape[1] == N and t.numel() > 0:
-        C = t.shape[2]
-        sb, sn, sc = t.stride()
-        if (sc == 1 or C == 1) and sn >= C and (B == 1 or sb == N * sn):
-            return t, int(sn)
+    if t.dim() == 3:
+        stride = row_stride_of(tuple(t.shape), t.stride(), B, N)
+        if stride is not None:
+            return t, stride
     t = t.contiguous()
     return t, int(t.shape[-1]) if t.dim() else 0
 

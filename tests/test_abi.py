@@ -117,3 +117,24 @@ def test_host_argument_parsing():
         parse_stride([1, 0, 1])
     with pytest.raises(ValueError):
         parse_voxel([0.0])
+
+
+def test_row_stride_of_channel_slices():
+    """Host logic of the strided-row forward (conv3p_forward_ex_f32): which tensor layouts are passed through as
+    (pointer, row stride) and which are made contiguous."""
+    import torch
+    from pointwise_b200.ops import row_stride_of
+    B, N, W = 3, 5, 36
+    buf = torch.zeros(B, N, W)
+    def rs(t):
+        return row_stride_of(tuple(t.shape), t.stride(), B, N)
+    assert rs(buf) == W
+    assert rs(buf[:, :, 9:18]) == W                      # a channel slice of the concat buffer
+    assert rs(buf[:, :, 35:36]) == W                     # one channel
+    assert rs(torch.zeros(B, N, 9)) == 9                 # dense
+    assert rs(buf[:, ::2, :9]) is None                   # wrong N (and rows not uniformly spaced for this N)
+    assert rs(buf.transpose(1, 2)) is None               # shape mismatch
+    assert rs(torch.zeros(B, N, 9).transpose(0, 1).contiguous().transpose(0, 1)) is None   # batch stride not N * row
+    assert rs(buf[:, :, ::2]) is None                    # channels not contiguous
+    assert row_stride_of((1, N, 9), buf[:1, :, :9].stride(), 1, N) == W      # B == 1: batch stride is free
+    assert row_stride_of((B, N, 0), (0, 0, 1), B, N) is None                 # empty
