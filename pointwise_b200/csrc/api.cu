@@ -332,7 +332,7 @@ int conv3p_forward_ex_f32(const conv3p_geom_t* geom, const void* plan, const flo
     if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
     return launch_forward_tc(geom, v, input, filter, Cin, Cout, output, scratch, scratch_bytes, stream, io);
   }
-  if (engine() != 3 && small_channels_supported(Cin, Cout))
+  if (engine() != 3 && small_forward_supported(Cin, Cout))
     return launch_forward_small(geom, v, input, filter, Cin, Cout, output, stream, io);
   return launch_forward_simt(geom, v, input, filter, Cin, Cout, output, stream, io);
 }
@@ -388,7 +388,7 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
       if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
       st = launch_backward_input_tc(geom, v, grad_output, filter, Cin, Cout, grad_input, scratch,
                                     scratch_bytes, stream, g_store);
-    } else if (engine() != 3 && small_channels_supported(Cin, Cout)) {
+    } else if (engine() != 3 && small_backward_input_supported(Cin, Cout)) {
       st = launch_backward_input_small(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);
     } else {
       st = launch_backward_input_simt(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);

@@ -125,6 +125,8 @@ int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const flo
 
 // warp-per-point fp32 engine for the reference models' small channel counts (3, 9, 13, 36)
 bool small_channels_supported(int Cin, int Cout);
+bool small_forward_supported(int Cin, int Cout);         // per direction (36->13 forward yes, 13->36 grad_input no)
+bool small_backward_input_supported(int Cin, int Cout);
 bool small_backward_filter_supported(int Cin, int Cout);
 size_t backward_filter_small_scratch_bytes(int Cin, int Cout);
 int launch_forward_small(const conv3p_geom_t* g, const PlanView& v, const float* input, const float* filter,

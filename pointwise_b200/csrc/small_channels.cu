@@ -140,12 +140,14 @@ struct SC2Lists {
 };
 
 // Phase 1 of the second-version kernels, by one warp for the point in `row`: A[f][ch] = sum over the members of
-// cell f of w * src[member][ch] (w = 1 / members, or the list's weights), in copy 0 of the warp's A area.
-// Returns the mask of non-empty cells; `ok` = the point's list is complete.
-__device__ __forceinline__ unsigned sc2_aggregate(const SC2Lists& p, int row, int lane, int Csrc, int G, uint32_t s_A,
-                                                  uint32_t s_pre, uint32_t s_inv, bool& ok) {
+// cell f of w * src[member][ch] (w = 1 / members, or the list's weights) for the cells f0 <= f < f1, in copy 0 of
+// the warp's A area.  Csrc <= 32: G = 32 / Csrc member slots, one channel per lane; Csrc <= 64: one slot, two
+// channels per lane.  Returns the mask of non-empty cells of the range; `ok` = the point's list is complete.
+__device__ __forceinline__ unsigned sc2_aggregate(const SC2Lists& p, int row, int lane, int Csrc, int G, int f0, int f1,
+                                                  uint32_t s_A, uint32_t s_pre, uint32_t s_inv, bool& ok) {
   const int cell_words = C3P_NCELL * Csrc;
-  const int g = lane / Csrc, ch = lane - g * Csrc;
+  const int g = lane / Csrc, ch = lane - g * Csrc;     // (Csrc > 32: g == 0, ch == lane)
+  const bool two = Csrc > 32, second = two && lane + 32 < Csrc;
   const long long bg = p.begin[row];
   ok = bg + p.len[row] <= p.capacity;
   const int mine = (ok && lane < C3P_NCELL) ? __ldg(p.cnt + (size_t)row * C3P_NCELL + lane) : 0;
@@ -155,27 +157,31 @@ __device__ __forceinline__ unsigned sc2_aggregate(const SC2Lists& p, int row, in
     const int u = __shfl_up_sync(C3P_FULL_MASK, incl, o);
     if (lane >= o) incl += u;
   }
-  const int K = __shfl_sync(C3P_FULL_MASK, incl, 31);
-  const unsigned cells = __ballot_sync(C3P_FULL_MASK, mine > 0);
+  const int total = __shfl_sync(C3P_FULL_MASK, incl, 31);
+  const unsigned range = (f1 >= 32 ? ~0u : ((1u << f1) - 1u)) & ~((1u << f0) - 1u);
+  const unsigned cells = __ballot_sync(C3P_FULL_MASK, mine > 0) & range;
   __syncwarp();
   if (lane < C3P_NCELL) {
     sts_f32(s_pre + 4u * lane, __int_as_float(incl - mine));
     sts_f32(s_inv + 4u * lane, mine > 0 ? __fdiv_rn(1.f, (float)mine) : 0.f);
   }
-  if (lane == 31) sts_f32(s_pre + 4u * C3P_NCELL, __int_as_float(K));
-  for (int e = lane; e < G * cell_words; e += 32) sts_f32(s_A + 4u * e, 0.f);
+  if (lane == 31) sts_f32(s_pre + 4u * C3P_NCELL, __int_as_float(total));
+  for (int gg = 0; gg < G; ++gg)   // the range's part of every slot's copy
+    for (int e = f0 * Csrc + lane; e < f1 * Csrc; e += 32) sts_f32(s_A + 4u * (uint32_t)(gg * cell_words + e), 0.f);
   __syncwarp();
+  if (!cells) return 0u;
+  const int Kbeg = __float_as_int(lds_f32(s_pre + 4u * (uint32_t)f0)), K = __float_as_int(lds_f32(s_pre + 4u * (uint32_t)f1));
   if (g < G) {
     const uint32_t Ag = s_A + 4u * (uint32_t)(g * cell_words + ch);
     const int* rlist = p.rows + bg;
     const float* wlist = p.weights ? p.weights + bg : nullptr;
-    int cf = 0;                                        // cell of the member being accumulated
-    int next_start = __float_as_int(lds_f32(s_pre + 4u));   // pre[cf + 1]
-    float wc = lds_f32(s_inv);                         // 1 / members of cell cf
-    float acc = 0.f;
-    for (int e0 = g; e0 < K; e0 += 4 * G) {
+    int cf = f0;                                         // cell of the member being accumulated
+    int next_start = __float_as_int(lds_f32(s_pre + 4u * (uint32_t)(f0 + 1)));   // pre[cf + 1]
+    float wc = lds_f32(s_inv + 4u * (uint32_t)f0);       // 1 / members of cell cf
+    float acc = 0.f, acc2 = 0.f;
+    for (int e0 = Kbeg + g; e0 < K; e0 += 4 * G) {
       int j[4];
-      float w[4], x[4];
+      float w[4], x[4], x2[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int e = e0 + u * G;
@@ -183,49 +189,68 @@ __device__ __forceinline__ unsigned sc2_aggregate(const SC2Lists& p, int row, in
         w[u] = (wlist && e < K) ? __ldg(wlist + e) : 1.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) x[u] = (e0 + u * G < K) ? __ldg(p.src + (size_t)j[u] * p.src_stride + ch) : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const bool in = e0 + u * G < K;
+        const float* r = p.src + (size_t)j[u] * p.src_stride + ch;
+        x[u] = in ? __ldg(r) : 0.f;
+        x2[u] = (in && second) ? __ldg(r + 32) : 0.f;
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int e = e0 + u * G;
         if (e < K) {
-          if (e >= next_start) {                       // the member starts a later cell: close the current one
+          if (e >= next_start) {                         // the member starts a later cell: close the current one
             sts_f32(Ag + 4u * (uint32_t)(cf * Csrc), acc);
+            if (second) sts_f32(Ag + 4u * (uint32_t)(cf * Csrc + 32), acc2);
             acc = 0.f;
+            acc2 = 0.f;
             do {
               ++cf;
               next_start = __float_as_int(lds_f32(s_pre + 4u * (uint32_t)(cf + 1)));
             } while (e >= next_start);
             wc = lds_f32(s_inv + 4u * (uint32_t)cf);
           }
-          acc = fmaf(wlist ? w[u] : wc, x[u], acc);
+          const float ww = wlist ? w[u] : wc;
+          acc = fmaf(ww, x[u], acc);
+          acc2 = fmaf(ww, x2[u], acc2);
         }
       }
     }
-    if (g < K) sts_f32(Ag + 4u * (uint32_t)(cf * Csrc), acc);
+    if (Kbeg + g < K) {
+      sts_f32(Ag + 4u * (uint32_t)(cf * Csrc), acc);
+      if (second) sts_f32(Ag + 4u * (uint32_t)(cf * Csrc + 32), acc2);
+    }
   }
   __syncwarp();
   // fold the G copies into copy 0, fixed order
-  for (int e = lane; e < cell_words; e += 32) {
-    float v = lds_f32(s_A + 4u * e);
-    for (int gg = 1; gg < G; ++gg) v += lds_f32(s_A + 4u * (uint32_t)(gg * cell_words + e));
-    sts_f32(s_A + 4u * e, v);
+  if (G > 1) {
+    for (int e = f0 * Csrc + lane; e < f1 * Csrc; e += 32) {
+      float v = lds_f32(s_A + 4u * e);
+      for (int gg = 1; gg < G; ++gg) v += lds_f32(s_A + 4u * (uint32_t)(gg * cell_words + e));
+      sts_f32(s_A + 4u * e, v);
+    }
+    __syncwarp();
   }
-  __syncwarp();
   return cells;
 }
 
-constexpr int SC2_WARP_WORDS = C3P_NCELL * 32 + 64;   // per warp: A copies (<= 27 * 32 floats) | cell starts | 1 / members
+constexpr int SC2_MAXC = 64;                               // widest channel count of the second version
+// per warp: A copies (G * 27 * Csrc <= 27 * max(32, Csrc) floats) | cell starts (32 ints) | 1 / members (32 floats)
+__host__ __device__ inline int sc2_a_words(int Csrc) { return C3P_NCELL * (Csrc > 32 ? Csrc : 32); }
+__host__ __device__ inline int sc2_warp_words(int Csrc) { return sc2_a_words(Csrc) + 64; }
+
+__device__ __forceinline__ int sc2_slots(int C) { return C > 32 ? 1 : 32 / C; }
 
 __global__ void __launch_bounds__(SC_THREADS) k_small_gather_contract2(const SCArgs a) {
   extern __shared__ float sc2[];
   const int Csrc = a.Csrc, Nout = a.Nout;
   const int nWf = C3P_NCELL * Csrc * Nout;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int G = 32 / Csrc, KG = 32 / Nout;
+  const int G = sc2_slots(Csrc), KG = sc2_slots(Nout);
   // shared-window addresses, converted once (tc_common.cuh): filter | per warp: A copies, cell starts, 1 / members
   const uint32_t s_w = tc::smem_u32_once(sc2);                                   // [27][Csrc][Nout]
-  const uint32_t s_A = s_w + 4u * (uint32_t)(((nWf + 3) & ~3) + warp * SC2_WARP_WORDS);   // [G][27][Csrc]
-  const uint32_t s_pre = s_A + 4u * (C3P_NCELL * 32);                            // [28] ints, pre[27] = K
+  const uint32_t s_A = s_w + 4u * (uint32_t)(((nWf + 3) & ~3) + warp * sc2_warp_words(Csrc));   // [G][27][Csrc]
+  const uint32_t s_pre = s_A + 4u * (uint32_t)sc2_a_words(Csrc);                 // [28] ints, pre[27] = K
   const uint32_t s_inv = s_pre + 4u * 32;                                        // [27]
   for (int e = threadIdx.x; e < nWf; e += SC_THREADS) {
     const int n = e % Nout, k = (e / Nout) % Csrc, f = e / (Nout * Csrc);
@@ -233,8 +258,10 @@ __global__ void __launch_bounds__(SC_THREADS) k_small_gather_contract2(const SCA
                           : a.filter[((size_t)f * a.Cin + k) * a.Cout + n];
   }
   __syncthreads();
+  // outputs: Nout <= 32: lanes = (k group, n); Nout <= 64: lanes = n and n + 32, one k group
   const int kg = lane / Nout, nn = lane - kg * Nout;
   const bool out_on = kg < KG;
+  const bool out2 = Nout > 32 && lane + 32 < Nout;
   SC2Lists L;
   L.src = a.src; L.cnt = a.cnt; L.begin = a.begin; L.len = a.len; L.rows = a.rows; L.weights = a.weights;
   L.src_stride = a.src_stride; L.capacity = a.capacity;
@@ -243,21 +270,29 @@ __global__ void __launch_bounds__(SC_THREADS) k_small_gather_contract2(const SCA
     const int b = (int)(s / a.N);
     const int row = b * a.N + __float_as_int(a.sorted_xyzi[s].w);
     bool ok;
-    const unsigned cells = sc2_aggregate(L, row, lane, Csrc, G, s_A, s_pre, s_inv, ok);
-    // ---- phase 2: out[n] = sum over non-empty cells f, channels k of A[f][k] * W_f[k][n]; lanes = (k group, n) -------
-    float o = 0.f;
+    const unsigned cells = sc2_aggregate(L, row, lane, Csrc, G, 0, C3P_NCELL, s_A, s_pre, s_inv, ok);
+    // ---- phase 2: out[n] = sum over non-empty cells f, channels k of A[f][k] * W_f[k][n] ------------------------------
+    float o = 0.f, o2 = 0.f;
     if (out_on) {
       for (unsigned todo = cells; todo; todo &= todo - 1) {
         const int f = __ffs(todo) - 1;
         const uint32_t af = s_A + 4u * (uint32_t)(f * Csrc), wf = s_w + 4u * (uint32_t)(f * Csrc * Nout + nn);
-        for (int k = kg; k < Csrc; k += KG) o = fmaf(lds_f32(af + 4u * k), lds_f32(wf + 4u * (uint32_t)(k * Nout)), o);
+        for (int k = kg; k < Csrc; k += KG) {
+          const float av = lds_f32(af + 4u * k);
+          o = fmaf(av, lds_f32(wf + 4u * (uint32_t)(k * Nout)), o);
+          if (out2) o2 = fmaf(av, lds_f32(wf + 4u * (uint32_t)(k * Nout + 32)), o2);
+        }
       }
     }
     // sum the KG partial sums in a fixed order (lanes nn, nn + Nout, nn + 2 Nout, ...)
-    float total = 0.f;
-    for (int q = 0; q < KG; ++q) total += __shfl_sync(C3P_FULL_MASK, o, (nn + q * Nout) & 31);
+    float total = o;
+    if (KG > 1) {
+      total = 0.f;
+      for (int q = 0; q < KG; ++q) total += __shfl_sync(C3P_FULL_MASK, o, (nn + q * Nout) & 31);
+    }
     const float nanv = __int_as_float(0x7fc00000);
     if (lane < Nout) a.out[(size_t)row * a.out_stride + lane] = ok ? apply_activation(total, a.activation) : nanv;
+    if (out2) a.out[(size_t)row * a.out_stride + lane + 32] = ok ? apply_activation(o2, a.activation) : nanv;
   }
 }
 
@@ -348,52 +383,60 @@ __global__ void __launch_bounds__(SC_THREADS) k_small_backward_filter(const SFAr
   }
 }
 
-// Second version of the weight gradient for Cin, Cout <= 16: the aggregate G_f[j, :] of every non-empty cell comes from
-// sc2_aggregate (whole list in flight, see above), then lanes = (k, c) pairs add the rank-1 update
-// x[j, k] * G_f[j, c] into the warp's private copy of grad_filter (plain read-modify-write, fixed order).
-__global__ void __launch_bounds__(SC_THREADS) k_small_backward_filter2(const SFArgs a) {
-  extern __shared__ float sf2[];   // [warps][27][Cin][Cout] private copies | per warp: A copies, cell starts, 1 / members
+// Second version of the weight gradient: the aggregate G_f[j, :] of every non-empty cell comes from sc2_aggregate
+// (whole list in flight, see above), then lanes = (k, c) pairs add the rank-1 update x[j, k] * G_f[j, c] into the
+// warp's private copy of grad_filter (plain read-modify-write, fixed order).  When 8 private copies of all 27 cells do
+// not fit in shared memory (36 x 13: 50 KB each) the cells are covered in passes of `cells_per_pass`; a pass walks
+// only its own cells' part of every list, so nothing is gathered twice.
+__global__ void __launch_bounds__(SC_THREADS) k_small_backward_filter2(const SFArgs a, int cells_per_pass) {
+  extern __shared__ float sf2[];   // [warps][cells_per_pass][Cin][Cout] private copies | per warp: A copies, cell starts, 1 / members
   const int Cin = a.Cin, Cout = a.Cout;
-  const int nW = C3P_NCELL * Cin * Cout;
+  const int pairs = Cin * Cout;
+  const int nWp = cells_per_pass * pairs;              // one private copy
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int G = 32 / Cout;
-  for (int e = threadIdx.x; e < SC_WARPS * nW; e += SC_THREADS) sf2[e] = 0.f;
-  __syncthreads();
+  const int G = sc2_slots(Cout);
   const uint32_t s_all = tc::smem_u32_once(sf2);
-  const uint32_t s_gw = s_all + 4u * (uint32_t)(warp * nW);
-  const uint32_t s_A = s_all + 4u * (uint32_t)(((SC_WARPS * nW + 3) & ~3) + warp * SC2_WARP_WORDS);
-  const uint32_t s_pre = s_A + 4u * (C3P_NCELL * 32), s_inv = s_pre + 4u * 32;
+  const uint32_t s_gw = s_all + 4u * (uint32_t)(warp * nWp);
+  const uint32_t s_A = s_all + 4u * (uint32_t)(((SC_WARPS * nWp + 3) & ~3) + warp * sc2_warp_words(Cout));
+  const uint32_t s_pre = s_A + 4u * (uint32_t)sc2_a_words(Cout), s_inv = s_pre + 4u * 32;
   SC2Lists L;
   L.src = a.grad_out; L.cnt = a.cnt; L.begin = a.begin; L.len = a.len; L.rows = a.rows; L.weights = a.weights;
   L.src_stride = Cout; L.capacity = a.capacity;
-  const int pairs = Cin * Cout;
   const long long stride = (long long)gridDim.x * SC_WARPS;
-  for (long long s = (long long)blockIdx.x * SC_WARPS + warp; s < a.total_points; s += stride) {
-    const int b = (int)(s / a.N);
-    const int row = b * a.N + __float_as_int(a.sorted_xyzi[s].w);
-    const float x = lane < Cin ? __ldg(a.input + (size_t)row * Cin + lane) : 0.f;
-    bool ok;
-    const unsigned cells = sc2_aggregate(L, row, lane, Cout, G, s_A, s_pre, s_inv, ok);
-    if (!ok) continue;   // (an incomplete list has no cells: the mask is empty anyway)
-    for (int p0 = 0; p0 < pairs; p0 += 32) {
-      const int p = p0 + lane;
-      const int k = p / Cout, c = p - k * Cout;
-      const float xk = __shfl_sync(C3P_FULL_MASK, x, k & 31);
-      if (p < pairs) {
-        for (unsigned todo = cells; todo; todo &= todo - 1) {
-          const int f = __ffs(todo) - 1;
-          const uint32_t at = s_gw + 4u * (uint32_t)(f * pairs + p);
-          sts_f32(at, fmaf(xk, lds_f32(s_A + 4u * (uint32_t)(f * Cout + c)), lds_f32(at)));
+  float* dst = a.partial + (size_t)blockIdx.x * C3P_NCELL * pairs;
+  for (int f0 = 0; f0 < C3P_NCELL; f0 += cells_per_pass) {
+    const int f1 = min(C3P_NCELL, f0 + cells_per_pass);
+    for (int e = threadIdx.x; e < SC_WARPS * nWp; e += SC_THREADS) sf2[e] = 0.f;
+    __syncthreads();
+    for (long long s = (long long)blockIdx.x * SC_WARPS + warp; s < a.total_points; s += stride) {
+      const int b = (int)(s / a.N);
+      const int row = b * a.N + __float_as_int(a.sorted_xyzi[s].w);
+      const float x0 = lane < Cin ? __ldg(a.input + (size_t)row * Cin + lane) : 0.f;
+      const float x1 = lane + 32 < Cin ? __ldg(a.input + (size_t)row * Cin + lane + 32) : 0.f;
+      bool ok;
+      const unsigned cells = sc2_aggregate(L, row, lane, Cout, G, f0, f1, s_A, s_pre, s_inv, ok);
+      if (!cells) continue;   // (an incomplete list has no cells either)
+      for (int p0 = 0; p0 < pairs; p0 += 32) {
+        const int p = p0 + lane;
+        const int k = p / Cout, c = p - k * Cout;
+        const float xa = __shfl_sync(C3P_FULL_MASK, x0, k & 31), xb = __shfl_sync(C3P_FULL_MASK, x1, k & 31);
+        const float xk = k < 32 ? xa : xb;
+        if (p < pairs) {
+          for (unsigned todo = cells; todo; todo &= todo - 1) {
+            const int f = __ffs(todo) - 1;
+            const uint32_t at = s_gw + 4u * (uint32_t)((f - f0) * pairs + p);
+            sts_f32(at, fmaf(xk, lds_f32(s_A + 4u * (uint32_t)(f * Cout + c)), lds_f32(at)));
+          }
         }
       }
     }
-  }
-  __syncthreads();
-  float* dst = a.partial + (size_t)blockIdx.x * nW;
-  for (int e = threadIdx.x; e < nW; e += SC_THREADS) {
-    float sum = 0.f;
-    for (int c = 0; c < SC_WARPS; ++c) sum += sf2[(size_t)c * nW + e];  // fixed order over the warps
-    dst[e] = sum;
+    __syncthreads();
+    for (int e = threadIdx.x; e < (f1 - f0) * pairs; e += SC_THREADS) {
+      float sum = 0.f;
+      for (int c = 0; c < SC_WARPS; ++c) sum += sf2[(size_t)c * nWp + e];  // fixed order over the warps
+      dst[(size_t)f0 * pairs + e] = sum;
+    }
+    __syncthreads();
   }
 }
 
@@ -414,21 +457,39 @@ static int sc_sms() {
 
 // Measured on B200 (profiles/r1_summary.md): the warp-per-point gather-contract wins up to ~16 channels (2x at
 // ModelNet40 densities), the tile engine from 36->13 up; the private-copy grad_filter kernel wins whenever it fits.
+// second version: both channel counts <= 64 and the filter + the warps' aggregate areas in shared memory; measured
+// against the tile engine it wins for the reference models' shapes (3->9, 9->9, 36->13); kept to Cin * Cout <= 512
+static bool sc2_shape(int Csrc, int Nout) {
+  return Csrc <= SC2_MAXC && Nout <= SC2_MAXC && Csrc * Nout <= 512;
+}
+// forward / grad_input: with more than 32 outputs (two per lane, one k group) the tile engine is faster
+// (13->36 grad_input at 16 x 4096 points: 0.39 ms against 0.41 ms)
+static bool sc2_gather_shape(int Csrc, int Nout) { return sc2_shape(Csrc, Nout) && Nout <= 32; }
 bool small_channels_supported(int Cin, int Cout) {
-  return Cin <= 16 && Cout <= 16;
+  if (engine() & 1024) return Cin <= 16 && Cout <= 16;   // first version only (A/B timing)
+  return sc2_gather_shape(Cin, Cout) && sc2_gather_shape(Cout, Cin);   // forward and grad_input both
+}
+bool small_forward_supported(int Cin, int Cout) {
+  if (engine() & 1024) return Cin <= 16 && Cout <= 16;
+  return sc2_gather_shape(Cin, Cout);
+}
+bool small_backward_input_supported(int Cin, int Cout) {
+  if (engine() & 1024) return Cin <= 16 && Cout <= 16;
+  return sc2_gather_shape(Cout, Cin);
 }
 bool small_backward_filter_supported(int Cin, int Cout) {
+  if (!(engine() & 1024) && sc2_shape(Cin, Cout)) return true;
   return Cin <= 40 && Cout <= 40 && (size_t)SC_WARPS * C3P_NCELL * Cin * Cout * 4 <= 96 * 1024;
 }
 
 static int launch_small_gc(SCArgs& a, const char* name, cudaStream_t stream) {
   if (a.total_points == 0) return CONV3P_OK;
-  if (a.Csrc <= 16 && a.Nout <= 16 && !(engine() & 1024)) {   // engine bit 1024: first version (A/B timing)
+  if (sc2_gather_shape(a.Csrc, a.Nout) && !(engine() & 1024)) {   // engine bit 1024: first version (A/B timing)
     const size_t smem2 = sizeof(float) * (((size_t)C3P_NCELL * a.Csrc * a.Nout + 3) / 4 * 4 +
-                                          (size_t)SC_WARPS * SC2_WARP_WORDS);
+                                          (size_t)SC_WARPS * sc2_warp_words(a.Csrc));
     if (smem2 > 40 * 1024)
       C3P_CUDA(cudaFuncSetAttribute(k_small_gather_contract2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    long long grid2 = (long long)sc_sms() * 4;
+    long long grid2 = (long long)sc_sms() * (smem2 > 100 * 1024 ? 1 : (smem2 > 48 * 1024 ? 2 : 4));
     const long long need2 = (a.total_points + SC_WARPS - 1) / SC_WARPS;
     if (grid2 > need2) grid2 = need2;
     {
@@ -496,8 +557,17 @@ int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, cons
   a.rows = v.bwd_row; a.weights = v.bwd_weight; a.sorted_xyzi = v.sorted_xyzi;
   a.partial = static_cast<float*>(scratch);
   a.total_points = pts; a.capacity = g->pair_capacity; a.N = g->N; a.Cin = Cin; a.Cout = Cout;
-  const bool v2 = Cin <= 16 && Cout <= 16 && !(engine() & 1024);   // engine bit 1024: first version (A/B timing)
-  const size_t smem = v2 ? sizeof(float) * (((size_t)SC_WARPS * nW + 3) / 4 * 4 + (size_t)SC_WARPS * SC2_WARP_WORDS)
+  const bool v2 = sc2_shape(Cin, Cout) && !(engine() & 1024);   // engine bit 1024: first version (A/B timing)
+  // second version: as many cells per pass as 8 private copies fit next to the aggregate areas with two CTAs per SM
+  int cells_per_pass = C3P_NCELL;
+  if (v2) {
+    const size_t per_cell = sizeof(float) * (size_t)SC_WARPS * Cin * Cout;
+    const size_t room = 112 * 1024 - sizeof(float) * (size_t)SC_WARPS * sc2_warp_words(Cout);
+    if (per_cell * C3P_NCELL > room) cells_per_pass = (int)(room / per_cell);
+    if (cells_per_pass < 1) cells_per_pass = 1;
+  }
+  const size_t smem = v2 ? sizeof(float) * (((size_t)SC_WARPS * cells_per_pass * Cin * Cout + 3) / 4 * 4 +
+                                            (size_t)SC_WARPS * sc2_warp_words(Cout))
                          : sizeof(float) * (size_t)SC_WARPS * nW;
   if (smem > 40 * 1024) {  // (static shared memory counts against the 48 KB default too)
     if (v2)
@@ -505,7 +575,7 @@ int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, cons
     else
       C3P_CUDA(cudaFuncSetAttribute(k_small_backward_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const int per_sm = smem > 100 * 1024 ? 1 : 2;
+  const int per_sm = smem > 113 * 1024 ? 1 : 2;
   int sms = sc_sms();
   if (sms > 256) sms = 256;
   long long grid = (long long)sms * per_sm;
@@ -514,7 +584,7 @@ int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, cons
   {
     LaunchTimer timer_("k_small_backward_filter", stream);
     if (v2)
-      k_small_backward_filter2<<<(unsigned)grid, SC_THREADS, smem, stream>>>(a);
+      k_small_backward_filter2<<<(unsigned)grid, SC_THREADS, smem, stream>>>(a, cells_per_pass);
     else
       k_small_backward_filter<<<(unsigned)grid, SC_THREADS, smem, stream>>>(a);
   }
