@@ -22,6 +22,9 @@
 //
 // Warp roles: warps [0, NPW) producers (also the epilogue), NPW = MMA issuer, NPW+1 = weight loader + TMEM
 // allocator, NPW+2 = item-list loader.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_gather2.cuh"
@@ -51,6 +54,7 @@ struct G2Args {
   long long total_points, subtiles;
   int N, Csrc, Nout, nkb, T, NAS, NWU;
   int debug;  // bit 32: accumulate the phase timers below
+  int res_big, res_one;  // scheduler: sub-tiles kept back for chunks smaller than T / for single sub-tiles, in units of G/2
   long long src_stride, out_stride;  // floats between gathered rows / output rows (multiples of 4)
   int activation;                    // epilogue: CONV3P_ACT_*
   // WEIGHTED only, optional: the aggregated rows G_f[j, :] of every non-empty (point, cell) are also written to
@@ -253,9 +257,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
   __shared__ int s_T;
   const long long G = gridDim.x;
   const int Tmax = a.T;
-  const long long n_big = a.subtiles > 6 * G ? (a.subtiles - 6 * G) / Tmax : 0;         // chunks of Tmax
+  const long long keep_big = a.res_big * G / 2, keep_one = a.res_one * G / 2;
+  const long long n_big = a.subtiles > keep_big ? (a.subtiles - keep_big) / Tmax : 0;   // chunks of Tmax
   const long long r1 = a.subtiles - n_big * Tmax;
-  const long long n_mid = (Tmax >= 2 && r1 > 2 * G) ? (r1 - 2 * G) / 2 : 0;                            // chunks of 2
+  const long long n_mid = (Tmax >= 2 && r1 > keep_one) ? (r1 - keep_one) / 2 : 0;                      // chunks of 2
   const long long n_one = r1 - n_mid * 2;                                               // chunks of 1
   auto claim = [&]() {
     const long long k = (long long)atomicAdd(a.counter, 1u);
@@ -644,6 +649,11 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
   a.nkb = c.nkb; a.T = c.T; a.NAS = c.NAS; a.NWU = c.NWU;
   a.debug = engine() >= 64 ? (engine() & ~(64 | 128 | 256)) : 0;
   a.g_store = weighted ? g_store : nullptr;
+  a.res_big = 12; a.res_one = 4;   // 6 G and 2 G sub-tiles (tuned at 2048 sub-tiles; CONV3P_SCHED="big,one" overrides for sweeps)
+  if (const char* e = getenv("CONV3P_SCHED")) {
+    int x = 0, y = 0;
+    if (sscanf(e, "%d,%d", &x, &y) == 2 && x >= y && y >= 0) { a.res_big = x; a.res_one = y; }
+  }
   a.src_stride = io.src_stride ? io.src_stride : Csrc;
   a.out_stride = io.out_stride ? io.out_stride : Nout;
   a.activation = io.activation;
