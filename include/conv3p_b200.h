@@ -45,7 +45,8 @@ enum {
   CONV3P_ERR_CUDA = 3,             /* a CUDA runtime call failed; see conv3p_last_cuda_error */
   CONV3P_ERR_UNSUPPORTED = 4,      /* e.g. filter not 3x3x3 */
   CONV3P_ERR_PAIR_OVERFLOW = 5,    /* reported by conv3p_plan_stats: pair_capacity too small */
-  CONV3P_ERR_NO_BACKWARD_LISTS = 6 /* backward called before conv3p_plan_build_backward */
+  CONV3P_ERR_NO_BACKWARD_LISTS = 6 /* conv3p_backward_f32 on a plan that conv3p_plan_build_f32 built in this process
+                                      and conv3p_plan_build_backward has not completed (tracked per plan address) */
 };
 
 /* Geometry of one call: B clouds of N points, the dilation stride per axis (x,y,z), the voxel size
@@ -135,7 +136,7 @@ int conv3p_forward_ex_f32(const conv3p_geom_t* geom, const void* plan, const flo
                           conv3p_stream_t stream);
 
 /* out[r, c] = grad[r, c] * selu'(x) expressed through the ACTIVATED value y = selu(x) the forward stored:
- * scale for y > 0, y + scale*alpha otherwise.  y and grad rows may be strided (floats; 0 = dense); out is dense
+ * scale for y >= 0 (the reference's SELU takes the linear branch for x >= 0, selu.py:25), y + scale*alpha otherwise.  y and grad rows may be strided (floats; 0 = dense); out is dense
  * [rows, C].  The backward of the fused epilogue: feed `out` to conv3p_backward_f32 as grad_output. */
 int conv3p_selu_backward_f32(const float* y, long long y_row_stride, const float* grad, long long grad_row_stride,
                              float* out, long long rows, int C, conv3p_stream_t stream);
@@ -205,12 +206,19 @@ const char* conv3p_last_cuda_error(void); /* thread-local text of the last CONV3
 int conv3p_abi_version(void);
 /* Number of kernels this library launched on behalf of the calling thread since the last reset. */
 long long conv3p_launch_count(int reset);
-/* Selects the contraction engine: 0 = auto, 1 = fp32 SIMT only (tile engine or warp-per-point engine by
- * channel count), 2 = tensor cores (3xTF32) where supported, 3 = generic fp32 tile engine only.  Values
- * >= 64 carry profiling/ablation bits for A/B timing (tools/engine_timing.py, tools/ab_backward.py): 32|64 phase
- * timers of the gather+MMA kernel, 128 first-generation tensor-core kernels, 256 no G store shared between the two
- * gradient kernels.  Returns the previous value.  Process-wide. */
+/* Selects the contraction engine.  Low three bits: 0 = auto (tensor cores where the shape is a real dense GEMM, else
+ * the fp32 engines), 1 = fp32 SIMT only (warp-per-point or tile kernels by channel count), 2 = tensor cores (3xTF32)
+ * where supported, 3 = generic fp32 tile kernels only (no tensor cores, no warp-per-point kernels).  Higher bits are
+ * ablation flags for A/B timing (tools/engine_timing.py, tools/ab_backward.py): 32 = phase timers of the gather+MMA
+ * kernel, 256 = no G store shared between the two gradient kernels, 1024 = first version of the small-channel
+ * kernels.  Returns the previous value.  Process-wide (a test/benchmark knob, not part of the operator's state). */
 int conv3p_set_engine(int engine);
+
+/* Profiling helpers of tools/engine_timing.py: read and clear the device-side cycle counters the gather+MMA kernel
+ * accumulates while engine flag 32 is set (8 phase sums; sum and max of a CTA's total cycles).  HOST pointers.
+ * Synchronise the device. */
+int conv3p_debug_phase_cycles(unsigned long long* host8);
+int conv3p_debug_cta_cycles(unsigned long long* host2);
 
 /* Per-kernel timing for benchmarks: while enabled, every kernel launch is bracketed by CUDA events
  * on its stream.  conv3p_profile_enable(on) clears the records and returns the previous state.

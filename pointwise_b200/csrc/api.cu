@@ -2,7 +2,10 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 #include <cstdio>
 #include <cstring>
@@ -22,7 +25,77 @@ int cuda_fail(cudaError_t e, const char* what) {
   return CONV3P_ERR_CUDA;
 }
 void count_launch(int n) { g_launches += n; }
-int engine() { return g_engine.load(); }
+int engine() { return g_engine.load(std::memory_order_relaxed); }
+
+// ---- per-device facts and per-kernel attributes, resolved once ------------------------------------------
+int sm_count() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    (void)cudaGetLastError();
+    return 148;
+  }
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) {
+    (void)cudaGetLastError();
+    n = 148;
+  }
+  cached[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;   // (kernel, device) -> bytes granted
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaGetDevice");
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = done[std::make_pair(kernel, dev)];
+  if (have >= bytes) return CONV3P_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  have = bytes;
+  return CONV3P_OK;
+}
+
+// ---- which plans have backward lists (host-side mirror of header[H_HAS_BWD]) ------------------------------
+// The entry points are called in stream order, so the state of a plan buffer can be tracked per address without
+// reading the device: conv3p_plan_build_f32 marks it "forward lists only", conv3p_plan_build_backward "complete".
+// Unknown addresses (a plan built elsewhere and copied) are given the benefit of the doubt.
+static std::mutex g_plan_mutex;
+static std::unordered_map<const void*, bool> g_plan_has_bwd;
+static void plan_mark(const void* plan, bool has_bwd) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  if (g_plan_has_bwd.size() > 4096) g_plan_has_bwd.clear();   // bounded: addresses recycle
+  g_plan_has_bwd[plan] = has_bwd;
+}
+static bool plan_known_without_backward(const void* plan) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  auto it = g_plan_has_bwd.find(plan);
+  return it != g_plan_has_bwd.end() && !it->second;
+}
+
+// ---- ordered reduction of grad_filter partials, NaN when the plan's lists overflowed ------------------------
+__global__ void k_reduce_partials(const float* __restrict__ partial, int S, long long nW, float* __restrict__ out,
+                                  const long long* __restrict__ header) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nW) return;
+  float s = 0.f;
+  for (int i = 0; i < S; ++i) s += partial[(size_t)i * nW + w];  // fixed order: deterministic
+  if (header && header[H_OVERFLOW] != 0) s = __int_as_float(0x7fc00000);
+  out[w] = s;
+}
+
+int launch_reduce_partials(const float* partial, int S, long long nW, float* out, const long long* plan_header,
+                           cudaStream_t stream) {
+  {
+    LaunchTimer timer_("k_reduce_partials", stream);
+    k_reduce_partials<<<(unsigned)((nW + 255) / 256), 256, 0, stream>>>(partial, S, nW, out, plan_header);
+  }
+  C3P_LAUNCH_CHECK("k_reduce_partials");
+  return CONV3P_OK;
+}
 
 // ---- optional per-kernel event timing ---------------------------------------------------------------
 struct TimedLaunch {
@@ -147,7 +220,8 @@ static conv3p_geom_t make_geom(int B, int N, const int stride[3], float voxel, l
   return g;
 }
 
-// out[r, c] = grad[r, c] * selu'(x), from the activated value y = selu(x): scale if y > 0 else y + scale * alpha
+// out[r, c] = grad[r, c] * selu'(x), from the activated value y = selu(x): scale if y >= 0 (x >= 0, selu.py:25) else
+// y + scale * alpha
 __global__ void k_selu_backward(const float* __restrict__ y, long long ys, const float* __restrict__ g, long long gs,
                                 float* __restrict__ out, long long rows, int C) {
   const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
@@ -156,7 +230,7 @@ __global__ void k_selu_backward(const float* __restrict__ y, long long ys, const
     const long long r = e / C;
     const int c = (int)(e - r * C);
     const float yv = __ldg(y + r * ys + c);
-    out[e] = __ldg(g + r * gs + c) * (yv > 0.f ? scale : yv + scale * alpha);
+    out[e] = __ldg(g + r * gs + c) * (yv >= 0.f ? scale : yv + scale * alpha);   // selu.py:25: linear branch for x >= 0
   }
 }
 
@@ -245,6 +319,7 @@ int conv3p_plan_build_f32(const conv3p_geom_t* geom, const float* points, void* 
   int st = make_view(geom, plan, plan_bytes, &v);
   if (st) return st;
   if (!points && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
+  plan_mark(plan, false);
   st = launch_cloud_sort(geom, points, v, stream);
   if (st) return st;
   return launch_neighbor_search(geom, v, stream);
@@ -255,9 +330,11 @@ int conv3p_plan_build_backward(const conv3p_geom_t* geom, const float* points, v
   PlanView v;
   int st = make_view(geom, plan, plan_bytes, &v);
   if (st) return st;
+  if (!points && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
   st = launch_backward_lists(geom, points, v, stream);
   if (st) return st;
   C3P_CUDA(cudaMemsetAsync(v.header + H_HAS_BWD, 1, sizeof(long long), stream));
+  plan_mark(plan, true);
   return CONV3P_OK;
 }
 
@@ -285,10 +362,6 @@ size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
   size_t filt = backward_filter_scratch_bytes(geom, Cin, Cout);
   if (small_backward_filter_supported(Cin, Cout)) {
     const size_t t = backward_filter_small_scratch_bytes(Cin, Cout);
-    if (t > filt) filt = t;
-  }
-  if (backward_filter_tc_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
-    const size_t t = backward_filter_tc_scratch_bytes(geom, Cin, Cout);
     if (t > filt) filt = t;
   }
   if (backward_filter2_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
@@ -325,14 +398,12 @@ int conv3p_forward_ex_f32(const conv3p_geom_t* geom, const void* plan, const flo
   const long long ls = io.src_stride ? io.src_stride : Cin, lo = io.out_stride ? io.out_stride : Cout;
   const bool rows_aligned = ls % 4 == 0 && lo % 4 == 0 && reinterpret_cast<uintptr_t>(input) % 16 == 0 &&
                             reinterpret_cast<uintptr_t>(output) % 16 == 0;
-  const bool dense = !io.src_stride && !io.out_stride && !io.activation;
-  // tensor cores: the second-generation kernel takes strided rows and the epilogue, the first generation dense rows only
-  if (engine() != 1 && forward_tc_supported(geom->N, geom->pair_capacity, Cin, Cout) && rows_aligned &&
-      (dense || (!(engine() & 128) && gather_mma2_supported(geom->N, geom->pair_capacity, Cin, Cout)))) {
+  // tensor cores need 16-byte aligned rows; other layouts fall back to the fp32 engines
+  if (engine_allows_tc() && rows_aligned && forward_tc_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
     if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
     return launch_forward_tc(geom, v, input, filter, Cin, Cout, output, scratch, scratch_bytes, stream, io);
   }
-  if (engine() != 3 && small_forward_supported(Cin, Cout))
+  if (engine_allows_small() && small_forward_supported(Cin, Cout))
     return launch_forward_small(geom, v, input, filter, Cin, Cout, output, stream, io);
   return launch_forward_simt(geom, v, input, filter, Cin, Cout, output, stream, io);
 }
@@ -372,23 +443,34 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
   st = make_view(geom, plan, conv3p_plan_bytes(geom), &v);
   if (st) return st;
   if (!grad_output && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
-  // both gradients on the tensor-core kernels: the grad_input kernel leaves its aggregated rows in the G store
-  // (tail of the scratch buffer) for the grad_filter kernel; engine bit 256 switches the sharing off (A/B timing)
+  if (plan_known_without_backward(plan)) return CONV3P_ERR_NO_BACKWARD_LISTS;
+  if ((long long)geom->B * geom->N == 0) {
+    if (grad_filter) C3P_CUDA(cudaMemsetAsync(grad_filter, 0, sizeof(float) * C3P_NCELL * (size_t)Cin * Cout, stream));
+    return CONV3P_OK;
+  }
+  // Engine per gradient.  The tensor-core kernels use 16-byte vector accesses; other layouts run on the fp32 engines.
+  const bool aligned = reinterpret_cast<uintptr_t>(grad_output) % 16 == 0 && Cin % 4 == 0 && Cout % 4 == 0 &&
+                       reinterpret_cast<uintptr_t>(grad_input) % 16 == 0 && reinterpret_cast<uintptr_t>(input) % 16 == 0;
+  const bool gi_tc = grad_input && engine_allows_tc() && aligned &&
+                     backward_input_tc_supported(geom->N, geom->pair_capacity, Cin, Cout);
+  const bool gf_tc = grad_filter && engine_allows_tc() && aligned &&
+                     backward_filter2_supported(geom->N, geom->pair_capacity, Cin, Cout);
+  // Both gradients on the tensor-core kernels: the grad_input kernel leaves its aggregated rows in the G store (tail of
+  // the scratch buffer) for the grad_filter kernel -- only when BOTH launches below really take that pair of kernels.
+  // Engine bit 256 switches the sharing off (A/B timing).
   float* g_store = nullptr;
-  {
+  if (gi_tc && gf_tc && !engine_flag(256)) {
     const size_t gsb = g_store_bytes(geom, Cin, Cout);
     const size_t base = conv3p_scratch_bytes(geom, Cin, Cout);
-    if (grad_input && grad_filter && gsb && scratch && scratch_bytes >= base + gsb && engine() != 1 &&
-        !(engine() & (128 | 256)))
-      g_store = reinterpret_cast<float*>(static_cast<char*>(scratch) + base);
+    if (gsb && scratch && scratch_bytes >= base + gsb) g_store = reinterpret_cast<float*>(static_cast<char*>(scratch) + base);
   }
   if (grad_input) {
     if (!filter) return CONV3P_ERR_INVALID_ARGUMENT;
-    if (engine() != 1 && backward_input_tc_supported(geom->N, geom->pair_capacity, Cin, Cout)) {
+    if (gi_tc) {
       if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
       st = launch_backward_input_tc(geom, v, grad_output, filter, Cin, Cout, grad_input, scratch,
                                     scratch_bytes, stream, g_store);
-    } else if (engine() != 3 && small_backward_input_supported(Cin, Cout)) {
+    } else if (engine_allows_small() && small_backward_input_supported(Cin, Cout)) {
       st = launch_backward_input_small(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);
     } else {
       st = launch_backward_input_simt(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);
@@ -396,16 +478,13 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
     if (st) return st;
   }
   if (grad_filter) {
-    if (!input && (long long)geom->B * geom->N > 0) return CONV3P_ERR_INVALID_ARGUMENT;
+    if (!input) return CONV3P_ERR_INVALID_ARGUMENT;
     const size_t wpb = weight_panel_bytes(Cin, Cout) + tc_items_bytes(geom, Cin, Cout);
     if (!scratch || scratch_bytes < wpb) return CONV3P_ERR_BUFFER_TOO_SMALL;
-    if (engine() != 1 && !(engine() & 128) && backward_filter2_supported(geom->N, geom->pair_capacity, Cin, Cout))
+    if (gf_tc)
       st = launch_backward_filter2(geom, v, grad_output, input, Cin, Cout, grad_filter,
                                    static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream, g_store);
-    else if (engine() != 1 && backward_filter_tc_supported(geom->N, geom->pair_capacity, Cin, Cout))
-      st = launch_backward_filter_tc(geom, v, grad_output, input, Cin, Cout, grad_filter,
-                                     static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);
-    else if (engine() != 3 && small_backward_filter_supported(Cin, Cout))
+    else if (engine_allows_small() && small_backward_filter_supported(Cin, Cout))
       st = launch_backward_filter_small(geom, v, grad_output, input, Cin, Cout, grad_filter,
                                         static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);
     else

@@ -133,15 +133,6 @@ __global__ void __launch_bounds__(BF_THREADS) k_backward_filter(const BFArgs a) 
   }
 }
 
-__global__ void k_reduce_partials(const float* __restrict__ partial, int S, long long nW,
-                                  float* __restrict__ out) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nW) return;
-  float s = 0.f;
-  for (int i = 0; i < S; ++i) s += partial[(size_t)i * nW + w];  // fixed order: deterministic
-  out[w] = s;
-}
-
 struct BFConfig {
   int TK, TC, nTx, nTy, KB, CB, nKB, nCB, S, tiles_per_split;
 };
@@ -200,9 +191,10 @@ int launch_backward_filter_simt(const conv3p_geom_t* g, const PlanView& v, const
   const size_t smem = sizeof(float) * (size_t)BF_P * (c.KB + c.CB);
   dim3 grid(C3P_NCELL, c.S, c.nKB * c.nCB);
   if (c.TK == 4) {
-    if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default too)
-      C3P_CUDA(cudaFuncSetAttribute(k_backward_filter<4, 8>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) {  // (static shared memory counts against the 48 KB default too)
+      const int st = ensure_dynamic_smem(k_backward_filter<4, 8>, smem);
+      if (st) return st;
+    }
     {
     LaunchTimer timer_("k_backward_filter", stream);
     k_backward_filter<4, 8><<<grid, BF_THREADS, smem, stream>>>(a);
@@ -214,13 +206,7 @@ int launch_backward_filter_simt(const conv3p_geom_t* g, const PlanView& v, const
   }
   }
   C3P_LAUNCH_CHECK("k_backward_filter");
-  const int rt = 256;
-  {
-    LaunchTimer timer_("k_reduce_partials", stream);
-    k_reduce_partials<<<(unsigned)((nW + rt - 1) / rt), rt, 0, stream>>>(a.partial, c.S, nW, grad_filter);
-  }
-  C3P_LAUNCH_CHECK("k_reduce_partials");
-  return CONV3P_OK;
+  return launch_reduce_partials(a.partial, c.S, nW, grad_filter, v.header, stream);
 }
 
 }  // namespace c3p

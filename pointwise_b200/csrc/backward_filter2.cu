@@ -1,23 +1,27 @@
-// backward_filter2.cu -- second-generation weight gradient on the 5th-gen tensor cores.
+// backward_filter2.cu -- weight gradient on the 5th-gen tensor cores.
 //
 //   grad_filter[f, k, c] = sum_j input[j, k] * G_f[j, c],    G_f[j, :] = sum_{(ii,w) in cell f of j} w * grad_out[ii, :]
 //
-// (tf_conv3p_atrous.cpp:694-696 regrouped by (j, f'); same maths and the same MN-major 3xTF32 MMA as
-// backward_filter_tc.cu: D_f[c, k] += G_f^T X, M = Cout = 128, N = Cin, K = 8 points per instruction, persistent CTA
-// per SM, up to 512/Cin per-cell accumulators in TMEM per pass, deterministic partial reduce.)  What changed is the
-// CUDA-core side, which bounded the first version:
-//  * work items come from k_group_items (64-point sub-tiles of the backward lists, compacted by population
-//    class) through a bulk-copy ring instead of per-visit prefix tables built by 64 threads with 29 dependent
-//    global loads each;
-//  * a quarter-warp gathers ALL 128 channels of its row (four 32-channel panels, two members per round), so
-//    list ids, weights and predicates are paid once per 512-byte row rather than once per 256 bytes, and the
-//    accumulation is packed FFMA2 with weight-0 padding instead of zero-selects;
-//  * when grad_input is computed in the same call by k_gather_mma2, that kernel has already aggregated exactly these
-//    G_f rows and left them in the G store ([sorted position][27][Cout], only non-empty (point, cell) slots are
-//    written): the producers then read ONE 512-byte row per non-empty item (prefetched one group ahead) instead of
-//    walking its list -- 4.2x fewer row reads on the bench cloud and no ids or weights (template FROM_STORE).
+// (tf_conv3p_atrous.cpp:694-696 regrouped by (j, f').)  The contraction runs over POINTS: for a tile of PTS
+// voxel-sorted points and one "virtual accumulator" the tensor core computes D[m, k] += A^T X with MN-major 3xTF32
+// operands (point index = panel row), M = 128 TMEM lanes, N = Cin, K = 8 points per instruction:
+//   * Cout >= 128: the 128 lanes are one 128-channel block of one cell (Cout = 256: two blocks per cell);
+//   * Cout <  128: the lanes stack 128 / Cout CELLS of Cout channels each -- different cells share the B operand X
+//     (the tile's input rows), so stacking keeps M = 128 without an M = 64 instruction or padded lanes.
+// 512 / Cin accumulators live in TMEM at once (a "pass" over the CTA's tiles); persistent CTA per SM, per-CTA
+// partials, deterministic ordered reduce (launch_reduce_partials).  Work items come from k_group_items (PTS-row
+// lists of the backward lists, compacted by population class) through a bulk-copy ring; a quarter-warp gathers all
+// the channels of its row (packed FFMA2, weight-0 padding).  When grad_input is computed in the same call by
+// k_gather_mma2, that kernel has already aggregated exactly these G_f rows and left them in the G store
+// ([sorted position][27][Cout], only non-empty (point, cell) slots are written): the producers then read ONE row
+// per non-empty item (prefetched one stage ahead) instead of walking its list (template FROM_STORE).
 //
-// Warp roles: warps [0, 16) producers (also the flush), 16 = MMA issuer + TMEM allocator, 17 = item-list loader.
+// Warp roles: warps [0, NPW) producers (also the flush), NPW = MMA issuer + TMEM allocator, NPW+1 = item-list loader;
+// NPW = PTS / 4 (one quarter-warp per point of the tile).
+#include <cstdio>
+#include <cstdlib>
+#include <utility>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_gather2.cuh"
@@ -26,12 +30,8 @@ namespace c3p {
 
 using namespace tc;
 
-constexpr int W2_NPW = 16;
-constexpr int W2_THREADS = (W2_NPW + 2) * 32;
-constexpr int W2_PTS = 64;                          // points per stage (contraction length of a stage)
-constexpr int W2_PANEL = W2_PTS * PANEL_ROW_BYTES;  // 8 KB: 64 rows x 32 fp32
-constexpr int W2_NIS = 4;                           // item-list slots
-constexpr int W2_GP = 4;                            // Cout == 128: four 32-channel panels of G
+constexpr int W2_NIS = 4;      // item-list slots
+constexpr int W2_MAX_NGS = 6;  // G ring stages
 constexpr int W2_END = -1;
 
 struct W2Args {
@@ -39,51 +39,75 @@ struct W2Args {
   const float* input;      // [B*N, Cin]
   const int* rows;         // backward lists: rows ii
   const float* weights;    // backward lists: 1 / count(ii, f')
-  const uint2* g_items;    // [tiles][27][64]
-  const int* g_rowid;      // [tiles*64]
+  const uint2* g_items;    // [tiles][27][PTS]
+  const int* g_rowid;      // [tiles*PTS]
   const unsigned* g_mask;  // [tiles] bit f: some point of the tile has members in cell f
   float* partial;          // [gridDim.x][27*Cin*Cout]
-  const float* g_store;    // FROM_STORE: G_f rows [tiles*64][27][Cout] written by k_gather_mma2
+  const float* g_store;    // FROM_STORE: G_f rows [tiles*PTS][27][Cout] written by k_gather_mma2
   long long total_points, tiles;
-  int Cin, Cout, FG;       // FG = accumulators (cells) per pass
+  int Cin, Cout;
+  int FG;    // accumulators per pass (512 / Cin)
+  int NGS;   // G ring stages
+  int NXB;   // X buffers (1 or 2)
 };
 
-template <bool FROM_STORE>
-__global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args a) {
+// GP = 32-channel panels of G per cell inside one accumulator (Cout = 32, 64: GP = 1, 2 and 4 / GP cells stacked;
+// Cout = 128, 256: GP = 4, one or two 128-channel blocks per cell).
+template <int GP>
+struct W2Map {
+  static constexpr int CS = 4 / GP;   // cells stacked in one accumulator
+  // number of virtual accumulators
+  __host__ __device__ static int count(int Cout) { return GP == 4 ? C3P_NCELL * (Cout / 128) : (C3P_NCELL + CS - 1) / CS; }
+  // sub-mask (CS bits) of the accumulator's cells that have members in a tile with cell mask m
+  __host__ __device__ static unsigned cells(unsigned m, int va, int Cout) {
+    if (GP == 4) return (m >> (va / (Cout / 128))) & 1u;
+    return (m >> (va * CS)) & ((1u << CS) - 1u);
+  }
+};
+
+template <bool FROM_STORE, int GP, int PTS>
+__global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(const W2Args a) {
+  constexpr int NPW = PTS / 4;                         // producer warps: one quarter-warp per row of the tile
+  constexpr int CS = W2Map<GP>::CS;
+  constexpr uint32_t PANEL = (uint32_t)PTS * PANEL_ROW_BYTES;   // PTS rows x 32 fp32
+  constexpr uint32_t g_half = 4u * PANEL;              // hi (or lo) part of a G stage: 4 panels = 128 lanes
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int Cin = a.Cin, Cout = a.Cout, FG = a.FG;
-  const int xp = Cin / 32;                              // panels of the input rows
-  constexpr uint32_t g_half = (uint32_t)W2_GP * W2_PANEL;   // hi (or lo) part of a G stage
-  const uint32_t x_half = (uint32_t)xp * W2_PANEL;
-  unsigned char* g_base = smem;                          // 2 stages x (hi, lo)
-  unsigned char* x_base = g_base + 4 * (size_t)g_half;   // 2 buffers x (hi, lo)
-  uint2* items = reinterpret_cast<uint2*>(x_base + 4 * (size_t)x_half);  // [NIS][64]
-  __shared__ uint64_t g_full[2], g_empty[2], x_full[2], x_empty[2], it_full[W2_NIS], it_empty[W2_NIS], acc_full,
-      acc_empty;
+  const int Cin = a.Cin, Cout = a.Cout, FG = a.FG, NGS = a.NGS, NXB = a.NXB;
+  const int xp = Cin / 32;                             // panels of the input rows
+  const int MB = GP == 4 ? Cout / 128 : 1;             // 128-channel blocks per cell
+  const int NVA = W2Map<GP>::count(Cout);
+  const uint32_t x_half = (uint32_t)xp * PANEL;
+  unsigned char* g_base = smem;                                     // NGS stages x (hi, lo)
+  unsigned char* x_base = g_base + (size_t)NGS * 2 * g_half;        // NXB buffers x (hi, lo)
+  uint2* items = reinterpret_cast<uint2*>(x_base + (size_t)NXB * 2 * x_half);  // [NIS][CS][PTS]
+  __shared__ uint64_t g_full[W2_MAX_NGS], g_empty[W2_MAX_NGS], x_full[2], x_empty[2], it_full[W2_NIS],
+      it_empty[W2_NIS], acc_full, acc_empty;
   __shared__ uint32_t tmem_slot;
-  __shared__ int hdr[W2_NIS];
+  __shared__ int hdr[W2_NIS];   // accumulator | cell sub-mask << 8 | tile (CTA-local) << 12, or W2_END
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long per_cta = (a.tiles + gridDim.x - 1) / gridDim.x;
   const long long tile_lo = (long long)blockIdx.x * per_cta;
   const long long tile_hi = min(a.tiles, tile_lo + per_cta);
-  const int npass = (C3P_NCELL + FG - 1) / FG;
+  const int npass = (NVA + FG - 1) / FG;
   const unsigned max_row = (unsigned)(a.total_points - 1);
 
-  if (warp == W2_NPW) {
+  if (warp == NPW) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&g_full[i], W2_NPW);
+      for (int i = 0; i < NGS; ++i) {
+        mbar_init(&g_full[i], NPW);
         mbar_init(&g_empty[i], 1);
-        mbar_init(&x_full[i], W2_NPW);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&x_full[i], NPW);
         mbar_init(&x_empty[i], 1);
       }
       for (int i = 0; i < W2_NIS; ++i) {
         mbar_init(&it_full[i], 1);
-        mbar_init(&it_empty[i], W2_NPW);
+        mbar_init(&it_empty[i], NPW);
       }
       mbar_init(&acc_full, 1);
-      mbar_init(&acc_empty, W2_NPW);
+      mbar_init(&acc_empty, NPW);
       mbar_fence_init();
     }
     __syncwarp();
@@ -94,104 +118,137 @@ __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (warp < W2_NPW) {
+  // mask of the pass's accumulators that have members in a tile with cell mask m (bit = accumulator - va0)
+  auto pass_vas = [&](unsigned m, int va0, int va1) -> unsigned {
+    unsigned r = 0;
+    for (int va = va0; va < va1; ++va)
+      if (W2Map<GP>::cells(m, va, Cout)) r |= 1u << (va - va0);
+    return r;
+  };
+
+  if (warp < NPW) {
     // =========================== producers ===========================================================
-    // Quarter-warp q serves row q of the tile for the input panels and item (q + 4g) mod 64 of group g.
+    // Quarter-warp q serves row q of the tile for the input panels and item (q + 4g) mod PTS of every cell of
+    // stage g.
     const int q = warp * 4 + (lane >> 3), l8 = lane & 7;
-    auto read_item = [&](int g_, G2Item& it) -> int {
+    struct Stage {
+      G2Item it[CS];
+      int h;   // header of the stage
+    };
+    auto read_stage = [&](int g_, Stage& s) {
       const int slot = g_ & (W2_NIS - 1);
       mbar_wait(&it_full[slot], (uint32_t)((g_ / W2_NIS) & 1));
-      const int h = hdr[slot];
-      const uint2 u = items[slot * W2_PTS + ((q + 4 * g_) & 63)];
+      s.h = hdr[slot];
+      const unsigned sub = s.h == W2_END ? 0u : ((unsigned)s.h >> 8) & 15u;
+#pragma unroll
+      for (int cs = 0; cs < CS; ++cs) {
+        const uint2 u = items[(slot * CS + cs) * PTS + ((q + 4 * g_) & (PTS - 1))];
+        G2Item& it = s.it[cs];
+        it.pos = u.x; it.p = (int)(u.y & 255u);
+        it.n = ((sub >> cs) & 1u) ? (int)(u.y >> 8) : 0;
+        if (!((sub >> cs) & 1u)) { it.pos = 0u; it.p = (q + 4 * g_) & (PTS - 1); }   // no list was loaded: own row, zeros
+        it.inv = 0.f; it.w = 0.f; it.ids = 0;
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&it_empty[slot]);
-      it.pos = u.x; it.p = (int)(u.y & 255u); it.n = h != W2_END ? (int)(u.y >> 8) : 0;
-      it.inv = 0.f; it.w = 0.f;
-      if (!FROM_STORE) g2_prefetch<true>(it, a.rows, a.weights, 0, l8, max_row);
-      return h;
-    };
-    // FROM_STORE: the item's aggregated row (hdr = tile-local index << 8 | cell)
-    auto fetch_row = [&](const G2Item& it, int h, float4 (&v)[W2_GP]) {
-      const float* src = a.g_store + (((size_t)(tile_lo + (h >> 8)) * W2_PTS + it.p) * C3P_NCELL + (h & 255)) * Cout +
-                         l8 * 4;
+      if (!FROM_STORE) {
 #pragma unroll
-      for (int kc = 0; kc < W2_GP; ++kc)
-        v[kc] = it.n > 0 ? ldg4(src + kc * PANEL_K) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int cs = 0; cs < CS; ++cs) g2_prefetch<true>(s.it[cs], a.rows, a.weights, 0, l8, max_row);
+      }
+    };
+    // FROM_STORE: the aggregated rows of the stage's items (index cs * GP + kc)
+    auto fetch_rows = [&](const Stage& s, float4 (&v)[4]) {
+      const int va = s.h & 255;
+      const long long tile = tile_lo + (s.h >> 12);
+#pragma unroll
+      for (int cs = 0; cs < CS; ++cs) {
+        const int f = GP == 4 ? va / MB : va * CS + cs;
+        const int ch0 = GP == 4 ? (va % MB) * 128 : 0;
+        const float* src = a.g_store + (((size_t)tile * PTS + s.it[cs].p) * C3P_NCELL + f) * Cout + ch0 + l8 * 4;
+#pragma unroll
+        for (int kc = 0; kc < GP; ++kc)
+          v[cs * GP + kc] = s.it[cs].n > 0 ? ldg4(src + kc * PANEL_K) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
     int visit = 0, g = 0;
-    // Look-ahead queue of work items: the next item, with its first list ids (gather mode) or its G row (store mode)
-    // in flight.  (Three rows of look-ahead were measured slower: the kernel is bound by shared-memory bandwidth --
-    // operand reads of the MMAs plus the panel stores -- not by the latency of the row loads, and the extra registers
-    // spill.)
-    constexpr int LOOK = 1;
-    G2Item ahead[LOOK];
-    float4 ahead_row[LOOK][W2_GP];
+    // One stage of look-ahead: the next stage's items, with their first list ids (gather mode) or their G rows
+    // (store mode) in flight.  (Three stages were measured slower: register moves of loaded values stall like
+    // uses, and the extra registers spill.)
+    Stage ahead;
+    float4 ahead_rows[4];
     int n_read = 0;
     bool ended = false;
-    auto pull = [&](G2Item& it, float4 (&r)[W2_GP]) {
+    auto pull = [&](Stage& s, float4 (&r)[4]) {
       if (ended) {                 // nothing is published after the END marker
-        it.n = 0; it.p = 0; it.pos = 0u;
+        s.h = W2_END;
+#pragma unroll
+        for (int cs = 0; cs < CS; ++cs) { s.it[cs].n = 0; s.it[cs].p = 0; s.it[cs].pos = 0u; }
         return;
       }
-      const int h = read_item(n_read++, it);
-      ended = h == W2_END;
-      if (FROM_STORE) fetch_row(it, ended ? 0 : h, r);
+      read_stage(n_read++, s);
+      ended = s.h == W2_END;
+      if (FROM_STORE && !ended) fetch_rows(s, r);
     };
-#pragma unroll
-    for (int d = 0; d < LOOK; ++d) pull(ahead[d], ahead_row[d]);
+    pull(ahead, ahead_rows);
     for (int pass = 0; pass < npass; ++pass) {
-      const int f0 = pass * FG, f1 = min(C3P_NCELL, f0 + FG);
-      const unsigned pass_bits = ((f1 - f0) == 32 ? ~0u : ((1u << (f1 - f0)) - 1u)) << f0;
+      const int va0 = pass * FG, va1 = min(NVA, va0 + FG);
       unsigned pass_mask = 0;
-      int xrow = tile_lo < tile_hi ? __ldg(a.g_rowid + tile_lo * W2_PTS + q) : -1;
-      unsigned mask_next = tile_lo < tile_hi ? __ldg(a.g_mask + tile_lo) & pass_bits : 0u;
+      int xrow = tile_lo < tile_hi ? __ldg(a.g_rowid + tile_lo * PTS + q) : -1;
+      unsigned mask_next = tile_lo < tile_hi ? pass_vas(__ldg(a.g_mask + tile_lo), va0, va1) : 0u;
       for (long long tile = tile_lo; tile < tile_hi; ++tile) {
         const unsigned mask = mask_next;
         const int row = xrow;
         if (tile + 1 < tile_hi) {  // prefetch the next visit's row id and mask
-          xrow = __ldg(a.g_rowid + (tile + 1) * W2_PTS + q);
-          mask_next = __ldg(a.g_mask + tile + 1) & pass_bits;
+          xrow = __ldg(a.g_rowid + (tile + 1) * PTS + q);
+          mask_next = pass_vas(__ldg(a.g_mask + tile + 1), va0, va1);
         }
         if (!mask) continue;
         pass_mask |= mask;
         // ---- input rows of the tile -> X panels (hi/lo) ---------------------------------------------------
         {
-          const int xb = visit & 1, use = visit >> 1;
+          const int xb = visit % NXB, use = visit / NXB;
           if (use >= 1) mbar_wait(&x_empty[xb], (uint32_t)((use - 1) & 1));
           unsigned char* xs = x_base + (size_t)xb * 2 * x_half;
           const float* xr = a.input + (size_t)(row >= 0 ? row : 0) * Cin + l8 * 4;
           for (int pnl = 0; pnl < xp; ++pnl) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row >= 0) v = ldg4(xr + pnl * PANEL_K);
-            g2_store_split(xs + (size_t)pnl * W2_PANEL + panel_chunk_offset_mn(q, l8), x_half, v);
+            g2_store_split(xs + (size_t)pnl * PANEL + panel_chunk_offset_mn(q, l8), x_half, v);
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&x_full[xb]);
         }
-        // ---- one G stage per active cell -----------------------------------------------------------------
+        // ---- one G stage per active accumulator -----------------------------------------------------------
         for (unsigned todo = mask; todo; todo &= todo - 1) {
-          G2Item cur = ahead[0];
-          float4 acc[W2_GP];
+          Stage cur = ahead;
+          float4 acc[4];
 #pragma unroll
-          for (int kc = 0; kc < W2_GP; ++kc) acc[kc] = ahead_row[0][kc];
+          for (int i = 0; i < 4; ++i) acc[i] = ahead_rows[i];
+          pull(ahead, ahead_rows);
+          const int slot = g % NGS, use = g / NGS;
+          unsigned char* stage = g_base + (size_t)slot * 2 * g_half;
+          bool waited = false;
 #pragma unroll
-          for (int d = 0; d + 1 < LOOK; ++d) {
-            ahead[d] = ahead[d + 1];
+          for (int cs = 0; cs < CS; ++cs) {
+            if (!FROM_STORE) {
+              int nmax = max(cur.it[cs].n, __shfl_xor_sync(C3P_FULL_MASK, cur.it[cs].n, 8));
+              nmax = max(nmax, __shfl_xor_sync(C3P_FULL_MASK, nmax, 16));
+              const int ch0 = GP == 4 ? ((cur.h & 255) % MB) * 128 : 0;
+              float4 part[GP];
+              g2_gather<GP, 8 / GP, true>(part, cur.it[cs], nmax, a.grad_out, Cout, ch0, a.rows, a.weights, l8, max_row);
 #pragma unroll
-            for (int kc = 0; kc < W2_GP; ++kc) ahead_row[d][kc] = ahead_row[d + 1][kc];
+              for (int kc = 0; kc < GP; ++kc) acc[cs * GP + kc] = part[kc];
+            }
+            if (!waited) {
+              if (use >= 1) mbar_wait(&g_empty[slot], (uint32_t)((use - 1) & 1));
+              waited = true;
+            }
+            unsigned char* dst = stage + panel_chunk_offset_mn(cur.it[cs].p, l8);
+#pragma unroll
+            for (int kc = 0; kc < GP; ++kc)
+              g2_store_split(dst + (size_t)(cs * GP + kc) * PANEL, g_half, acc[cs * GP + kc]);
           }
-          pull(ahead[LOOK - 1], ahead_row[LOOK - 1]);
-          if (!FROM_STORE) {
-            int nmax = max(cur.n, __shfl_xor_sync(C3P_FULL_MASK, cur.n, 8));
-            nmax = max(nmax, __shfl_xor_sync(C3P_FULL_MASK, nmax, 16));
-            g2_gather<W2_GP, 2, true>(acc, cur, nmax, a.grad_out, Cout, 0, a.rows, a.weights, l8, max_row);
-          }
-          const int slot = g & 1, use = g >> 1;
-          if (use >= 1) mbar_wait(&g_empty[slot], (uint32_t)((use - 1) & 1));
-          unsigned char* stage = g_base + (size_t)slot * 2 * g_half + panel_chunk_offset_mn(cur.p, l8);
-#pragma unroll
-          for (int kc = 0; kc < W2_GP; ++kc) g2_store_split(stage + (size_t)kc * W2_PANEL, g_half, acc[kc]);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&g_full[slot]);
@@ -199,16 +256,18 @@ __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args
         }
         ++visit;
       }
-      // ---- flush this pass's accumulators: partial[cta][f][k][c] = D_f[c][k] ------------------------------
+      // ---- flush this pass's accumulators: partial[cta][f][k][c] = D[lane(c), k] ----------------------------
       mbar_wait(&acc_full, (uint32_t)(pass & 1));
       tc_fence_after_sync();
       {
         const int sub = warp & 3;
-        for (int ai = warp >> 2; ai < f1 - f0; ai += 4) {
-          const int f = f0 + ai;
-          const int c = sub * 32 + lane;                // TMEM lane == output channel c
-          const bool live = (pass_mask >> f) & 1u;
-          float* dst = a.partial + ((size_t)blockIdx.x * C3P_NCELL + f) * Cin * Cout;
+        const int L = sub * 32 + lane;                     // TMEM lane
+        for (int ai = warp >> 2; ai < va1 - va0; ai += NPW / 4) {
+          const int va = va0 + ai;
+          const int f = GP == 4 ? va / MB : va * CS + L / (GP * 32);
+          const int c = GP == 4 ? (va % MB) * 128 + L : L % (GP * 32);
+          const bool live = (pass_mask >> ai) & 1u;
+          float* dst = a.partial + ((size_t)blockIdx.x * C3P_NCELL + (f < C3P_NCELL ? f : 0)) * Cin * Cout;
           for (int k0 = 0; k0 < Cin; k0 += 32) {
             float v[32];
             if (live) {
@@ -217,7 +276,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
-            if (c < Cout) {
+            if (f < C3P_NCELL) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) dst[(size_t)(k0 + j) * Cout + c] = v[j];
             }
@@ -228,45 +287,44 @@ __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty);
     }
-  } else if (warp == W2_NPW) {
+  } else if (warp == NPW) {
     // =========================== MMA issuer (one thread) ===============================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_mn(Cout, Cin);
+      const uint32_t idesc = make_idesc_tf32_mn(128, Cin);
       int visit = 0, gs = 0;
       for (int pass = 0; pass < npass; ++pass) {
-        const int f0 = pass * FG, f1 = min(C3P_NCELL, f0 + FG);
-        const unsigned pass_bits = ((f1 - f0) == 32 ? ~0u : ((1u << (f1 - f0)) - 1u)) << f0;
+        const int va0 = pass * FG, va1 = min(NVA, va0 + FG);
         unsigned started = 0;
         if (pass > 0) {
           mbar_wait(&acc_empty, (uint32_t)((pass - 1) & 1));
           tc_fence_after_sync();
         }
         for (long long tile = tile_lo; tile < tile_hi; ++tile) {
-          const unsigned mask = __ldg(a.g_mask + tile) & pass_bits;
+          const unsigned mask = pass_vas(__ldg(a.g_mask + tile), va0, va1);
           if (!mask) continue;
-          const int xb = visit & 1;
-          mbar_wait(&x_full[xb], (uint32_t)((visit >> 1) & 1));
+          const int xb = visit % NXB;
+          mbar_wait(&x_full[xb], (uint32_t)((visit / NXB) & 1));
           const uint32_t x_hi = smem_u32(x_base + (size_t)xb * 2 * x_half), x_lo = x_hi + x_half;
-          const int f_last = 31 - __clz(mask);
-          for (int f = f0; f < f1; ++f) {
-            if (!((mask >> f) & 1u)) continue;
-            const int slot = gs & 1;
-            mbar_wait(&g_full[slot], (uint32_t)((gs >> 1) & 1));
+          const int ai_last = 31 - __clz(mask);
+          for (unsigned todo = mask; todo; todo &= todo - 1) {
+            const int ai = __ffs(todo) - 1;
+            const int slot = gs % NGS;
+            mbar_wait(&g_full[slot], (uint32_t)((gs / NGS) & 1));
             tc_fence_after_sync();
             const uint32_t g_hi = smem_u32(g_base + (size_t)slot * 2 * g_half), g_lo = g_hi + g_half;
-            const uint32_t d = tmem + (uint32_t)((f - f0) * Cin);
+            const uint32_t d = tmem + (uint32_t)(ai * Cin);
 #pragma unroll
-            for (int j = 0; j < W2_PTS / 8; ++j) {
+            for (int j = 0; j < PTS / 8; ++j) {
               const uint32_t adv = (uint32_t)j * 1024u;  // 8 points further down the panels
-              const uint64_t dgh = make_smem_desc_mn(g_hi + adv, W2_PANEL), dgl = make_smem_desc_mn(g_lo + adv, W2_PANEL);
-              const uint64_t dxh = make_smem_desc_mn(x_hi + adv, W2_PANEL), dxl = make_smem_desc_mn(x_lo + adv, W2_PANEL);
-              mma_tf32(d, dgh, dxh, idesc, (((started >> f) & 1u) | (unsigned)j) ? 1u : 0u);
+              const uint64_t dgh = make_smem_desc_mn(g_hi + adv, PANEL), dgl = make_smem_desc_mn(g_lo + adv, PANEL);
+              const uint64_t dxh = make_smem_desc_mn(x_hi + adv, PANEL), dxl = make_smem_desc_mn(x_lo + adv, PANEL);
+              mma_tf32(d, dgh, dxh, idesc, (((started >> ai) & 1u) | (unsigned)j) ? 1u : 0u);
               mma_tf32(d, dgl, dxh, idesc, 1u);
               mma_tf32(d, dgh, dxl, idesc, 1u);
             }
-            started |= 1u << f;
+            started |= 1u << ai;
             mma_commit(&g_empty[slot]);
-            if (f == f_last) mma_commit(&x_empty[xb]);
+            if (ai == ai_last) mma_commit(&x_empty[xb]);
             ++gs;
           }
           ++visit;
@@ -279,17 +337,23 @@ __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args
     if (lane == 0) {
       int g = 0;
       for (int pass = 0; pass < npass; ++pass) {
-        const int f0 = pass * FG, f1 = min(C3P_NCELL, f0 + FG);
-        const unsigned pass_bits = ((f1 - f0) == 32 ? ~0u : ((1u << (f1 - f0)) - 1u)) << f0;
+        const int va0 = pass * FG, va1 = min(NVA, va0 + FG);
         for (long long tile = tile_lo; tile < tile_hi; ++tile) {
-          for (unsigned todo = __ldg(a.g_mask + tile) & pass_bits; todo; todo &= todo - 1) {
-            const int f = __ffs(todo) - 1;
+          const unsigned cellmask = __ldg(a.g_mask + tile);
+          for (unsigned todo = pass_vas(cellmask, va0, va1); todo; todo &= todo - 1) {
+            const int va = va0 + __ffs(todo) - 1;
+            const unsigned sub = W2Map<GP>::cells(cellmask, va, Cout);
             const int slot = g & (W2_NIS - 1), use = g / W2_NIS;
             if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
-            hdr[slot] = f | ((int)(tile - tile_lo) << 8);
-            mbar_arrive_expect_tx(&it_full[slot], W2_PTS * sizeof(uint2));
-            bulk_copy_g2s(items + slot * W2_PTS, a.g_items + (tile * C3P_NCELL + f) * W2_PTS,
-                          W2_PTS * sizeof(uint2), &it_full[slot]);
+            hdr[slot] = va | ((int)sub << 8) | ((int)(tile - tile_lo) << 12);
+            mbar_arrive_expect_tx(&it_full[slot], (uint32_t)__popc(sub) * PTS * (uint32_t)sizeof(uint2));
+#pragma unroll
+            for (int cs = 0; cs < CS; ++cs) {
+              if (!((sub >> cs) & 1u)) continue;
+              const int f = GP == 4 ? va / MB : va * CS + cs;
+              bulk_copy_g2s(items + (slot * CS + cs) * PTS, a.g_items + (tile * C3P_NCELL + f) * PTS,
+                            PTS * sizeof(uint2), &it_full[slot]);
+            }
             ++g;
           }
         }
@@ -302,43 +366,95 @@ __global__ void __launch_bounds__(W2_THREADS, 1) k_backward_filter2(const W2Args
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == W2_NPW) tmem_dealloc(tmem, 512);
+  if (warp == NPW) tmem_dealloc(tmem, 512);
 }
 
-__global__ void k_reduce_partials2(const float* __restrict__ partial, int S, long long nW,
-                                   float* __restrict__ out) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nW) return;
-  float s = 0.f;
-  for (int i = 0; i < S; ++i) s += partial[(size_t)i * nW + w];  // fixed order: deterministic
-  out[w] = s;
-}
+struct W2Config {
+  int GP, PTS, FG, NGS, NXB;
+  size_t smem;
+};
 
-static int w2_grid(long long tiles) {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  (void)cudaGetLastError();
-  if (sms < 1) sms = 148;
-  return (int)(tiles < sms ? (tiles < 1 ? 1 : tiles) : sms);
-}
-
-static size_t w2_smem_bytes(int Cin) {
-  return 4 * (size_t)W2_GP * W2_PANEL + 4 * (size_t)(Cin / 32) * W2_PANEL + W2_NIS * W2_PTS * sizeof(uint2);
+// Tile of 64 points when two G stages and the input panels fit next to each other, else 32; with the smaller tile
+// the ring takes as many stages as fit (up to W2_MAX_NGS).  CONV3P_W2="pts,stages" (read once) overrides for sweeps.
+static bool w2_config(int N, long long capacity, int Cin, int Cout, W2Config* c) {
+  if (N > 65535 || capacity >= (1LL << 32)) return false;
+  if (Cout != 32 && Cout != 64 && Cout != 128 && Cout != 256) return false;   // M = 128 lanes: see the header comment
+  if (Cin % 32 || Cin < 32 || Cin > 256) return false;                         // N of the MMA, in 32-wide MN-major panels
+  c->GP = Cout >= 128 ? 4 : Cout / 32;
+  c->FG = 512 / Cin;
+  static const std::pair<int, int> forced = [] {
+    std::pair<int, int> r(0, 0);
+    if (const char* e = getenv("CONV3P_W2")) {
+      int x = 0, y = 0;
+      if (sscanf(e, "%d,%d", &x, &y) == 2 && (x == 32 || x == 64) && y >= 2 && y <= W2_MAX_NGS) r = std::make_pair(x, y);
+    }
+    return r;
+  }();
+  const size_t budget = 227 * 1024 - 1024;
+  const int CS = 4 / c->GP;
+  // preference: 64-point tiles with two input buffers; else 32-point tiles (two input buffers, deeper ring); else a
+  // single input buffer
+  const int order[4][2] = {{64, 2}, {32, 2}, {64, 1}, {32, 1}};
+  for (int o = 0; o < 4; ++o) {
+    const int pts = order[o][0], nxb = order[o][1];
+    if (forced.first && pts != forced.first) continue;
+    const size_t panel = (size_t)pts * PANEL_ROW_BYTES;
+    const size_t g_stage = 2 * 4 * panel, x_buf = 2 * (size_t)(Cin / 32) * panel;
+    const size_t items = (size_t)W2_NIS * CS * pts * sizeof(uint2);
+    if (items + nxb * x_buf + 2 * g_stage > budget) continue;
+    int ngs = (int)((budget - items - nxb * x_buf) / g_stage);
+    if (ngs > W2_MAX_NGS) ngs = W2_MAX_NGS;
+    if (forced.second && forced.second <= ngs) ngs = forced.second;
+    c->PTS = pts; c->NGS = ngs; c->NXB = nxb;
+    c->smem = (size_t)ngs * g_stage + nxb * x_buf + items;
+    return true;
+  }
+  return false;
 }
 
 bool backward_filter2_supported(int N, long long capacity, int Cin, int Cout) {
-  if (N > 65535 || capacity >= (1LL << 32)) return false;
-  if (Cout != 128) return false;                         // M of the MMA (TMEM lane == channel)
-  if (Cin % 32 || Cin < 32 || Cin > 256) return false;   // N of the MMA, in 32-wide MN-major panels
-  return w2_smem_bytes(Cin) <= 227 * 1024 - 1024;
+  W2Config c;
+  return w2_config(N, capacity, Cin, Cout, &c);
 }
 
-// scratch: [64-row work-item lists | per-CTA partials (sized for up to 256 SMs so the query needs no device)]
+static int w2_grid(long long tiles) {
+  const int sms = sm_count();
+  return (int)(tiles < sms ? (tiles < 1 ? 1 : tiles) : sms);
+}
+
+// scratch: [PTS-row work-item lists | per-CTA partials (sized for up to 256 SMs so the query needs no device)]
 size_t backward_filter2_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout) {
+  W2Config c;
+  if (!w2_config(g->N, g->pair_capacity, Cin, Cout, &c)) return 0;
   const long long pts = (long long)g->B * g->N;
-  const long long tiles = (pts + W2_PTS - 1) / W2_PTS;
+  const long long tiles = (pts + c.PTS - 1) / c.PTS;
   const long long ctas = tiles < 256 ? (tiles < 1 ? 1 : tiles) : 256;
-  return group_items_bytes(pts, W2_PTS) + align_up(sizeof(float) * (size_t)ctas * C3P_NCELL * Cin * Cout);
+  return group_items_bytes(pts, c.PTS) + align_up(sizeof(float) * (size_t)ctas * C3P_NCELL * Cin * Cout);
+}
+
+template <bool FROM_STORE, int GP, int PTS>
+static int w2_launch(const W2Args& a, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = k_backward_filter2<FROM_STORE, GP, PTS>;
+  const int st = ensure_dynamic_smem(kern, 227 * 1024 - 1024);
+  if (st) return st;
+  {
+    LaunchTimer timer_("k_backward_filter_tc", stream);
+    kern<<<grid, (PTS / 4 + 2) * 32, smem, stream>>>(a);
+  }
+  C3P_LAUNCH_CHECK("k_backward_filter_tc");
+  return CONV3P_OK;
+}
+
+template <bool FROM_STORE>
+static int w2_dispatch(const W2Config& c, const W2Args& a, int grid, cudaStream_t stream) {
+  if (c.PTS == 64) {
+    if (c.GP == 4) return w2_launch<FROM_STORE, 4, 64>(a, grid, c.smem, stream);
+    if (c.GP == 2) return w2_launch<FROM_STORE, 2, 64>(a, grid, c.smem, stream);
+    return w2_launch<FROM_STORE, 1, 64>(a, grid, c.smem, stream);
+  }
+  if (c.GP == 4) return w2_launch<FROM_STORE, 4, 32>(a, grid, c.smem, stream);
+  if (c.GP == 2) return w2_launch<FROM_STORE, 2, 32>(a, grid, c.smem, stream);
+  return w2_launch<FROM_STORE, 1, 32>(a, grid, c.smem, stream);
 }
 
 int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const float* grad_out, const float* input,
@@ -350,10 +466,12 @@ int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const flo
     C3P_CUDA(cudaMemsetAsync(grad_filter, 0, sizeof(float) * nW, stream));
     return CONV3P_OK;
   }
+  W2Config c;
+  if (!w2_config(g->N, g->pair_capacity, Cin, Cout, &c)) return CONV3P_ERR_UNSUPPORTED;
   if (!scratch || scratch_bytes < backward_filter2_scratch_bytes(g, Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
-  const GroupItems gi = carve_group_items(scratch, pts, W2_PTS);
-  float* partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + group_items_bytes(pts, W2_PTS));
-  int st = launch_group_items(g, v, true, W2_PTS, gi, stream);
+  const GroupItems gi = carve_group_items(scratch, pts, c.PTS);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + group_items_bytes(pts, c.PTS));
+  int st = launch_group_items(g, v, true, c.PTS, gi, stream);
   if (st) return st;
   const int grid = w2_grid(gi.subtiles);
   if (grid > 256) return CONV3P_ERR_UNSUPPORTED;
@@ -361,24 +479,10 @@ int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const flo
   a.grad_out = grad_out; a.input = input; a.rows = v.bwd_row; a.weights = v.bwd_weight;
   a.g_items = gi.items; a.g_rowid = gi.rowid; a.g_mask = gi.mask; a.partial = partial; a.g_store = g_store;
   a.total_points = pts; a.tiles = gi.subtiles; a.Cin = Cin; a.Cout = Cout;
-  a.FG = 512 / Cin > 8 ? 8 : 512 / Cin;
-  const size_t smem = w2_smem_bytes(Cin);
-  if (g_store) {
-    C3P_CUDA(cudaFuncSetAttribute(k_backward_filter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LaunchTimer timer_("k_backward_filter_tc", stream);
-    k_backward_filter2<true><<<grid, W2_THREADS, smem, stream>>>(a);
-  } else {
-    C3P_CUDA(cudaFuncSetAttribute(k_backward_filter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LaunchTimer timer_("k_backward_filter_tc", stream);
-    k_backward_filter2<false><<<grid, W2_THREADS, smem, stream>>>(a);
-  }
-  C3P_LAUNCH_CHECK("k_backward_filter_tc");
-  {
-    LaunchTimer timer_("k_reduce_partials", stream);
-    k_reduce_partials2<<<(unsigned)((nW + 255) / 256), 256, 0, stream>>>(partial, grid, nW, grad_filter);
-  }
-  C3P_LAUNCH_CHECK("k_reduce_partials");
-  return CONV3P_OK;
+  a.FG = c.FG; a.NGS = c.NGS; a.NXB = c.NXB;
+  st = g_store ? w2_dispatch<true>(c, a, grid, stream) : w2_dispatch<false>(c, a, grid, stream);
+  if (st) return st;
+  return launch_reduce_partials(partial, grid, nW, grad_filter, v.header, stream);
 }
 
 }  // namespace c3p

@@ -55,7 +55,27 @@ struct LaunchTimer {
   cudaStream_t stream;
 };
 void count_launch(int n = 1);
+// conv3p_set_engine value: low three bits = contraction engine (0 auto, 1 fp32 SIMT, 2 tensor cores where the shape
+// allows, 3 generic fp32 tile kernels only); higher bits = ablation flags for A/B timing (see the header).
 int engine();
+inline int engine_kind() { return engine() & 7; }
+inline bool engine_flag(int bit) { return (engine() & bit) != 0; }
+inline bool engine_allows_tc() { return engine_kind() == 0 || engine_kind() == 2; }
+inline bool engine_allows_small() { return engine_kind() != 3; }
+
+// Per-device facts and per-kernel attributes, queried / set ONCE (not on every launch).
+int sm_count();                                   // multiprocessors of the current device (cached per device)
+int ensure_dynamic_smem(const void* kernel, size_t bytes);  // opt-in dynamic shared memory, once per (kernel, device)
+template <typename K>
+inline int ensure_dynamic_smem(K kernel, size_t bytes) {
+  return ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes);
+}
+
+// out[w] = sum_i partial[i][w] in a fixed order (deterministic).  When the plan's overflow flag is set (neighbour
+// lists incomplete because pair_capacity was too small) the weight gradient would silently miss terms: it is
+// poisoned with NaN instead, like the affected rows of output / grad_input.
+int launch_reduce_partials(const float* partial, int S, long long nW, float* out, const long long* plan_header,
+                           cudaStream_t stream);
 
 // stages (each enqueues kernels on `stream` and returns a status)
 int launch_cloud_sort(const conv3p_geom_t* g, const float* points, const PlanView& v,
@@ -87,7 +107,7 @@ int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* in
                       int Cin, int Cout, float* output, void* scratch, size_t scratch_bytes,
                       cudaStream_t stream, const RowIO& io = RowIO());
 
-// second-generation gather + MMA kernel (gather_mma2.cu); engine bit 128 selects the first generation instead
+// fused gather + MMA kernel (gather_mma2.cu)
 bool gather_mma2_supported(int N, long long capacity, int Csrc, int Nout);
 size_t gather_mma2_scratch_bytes(const conv3p_geom_t* g);  // work-item lists of one launch
 // Work-item lists of the tensor-core kernels (k_group_items): per sub-tile of `rows` voxel-sorted points and per
@@ -110,13 +130,7 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
 // scratch layout of one forward / backward call: [weight panel images | work-item lists | grad_filter partials]
 size_t tc_items_bytes(const conv3p_geom_t* g, int Cin, int Cout);
 
-bool backward_filter_tc_supported(int N, long long capacity, int Cin, int Cout);
-size_t backward_filter_tc_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout);
-int launch_backward_filter_tc(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
-                              const float* input, int Cin, int Cout, float* grad_filter, void* scratch,
-                              size_t scratch_bytes, cudaStream_t stream);
-
-// second-generation weight-gradient kernel (backward_filter2.cu)
+// weight-gradient kernel on tensor cores (backward_filter2.cu)
 bool backward_filter2_supported(int N, long long capacity, int Cin, int Cout);
 size_t backward_filter2_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout);
 int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const float* grad_out, const float* input,

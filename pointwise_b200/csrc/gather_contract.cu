@@ -192,7 +192,7 @@ static int launch_cfg(GCArgs& a, cudaStream_t stream) {
                       sizeof(long long) * a.P + sizeof(int) * ((size_t)a.P * 28 + a.P);
   auto kern = k_gather_contract<TP, TC>;
   if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default too)
-    C3P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int st_ = ensure_dynamic_smem(kern, smem); if (st_) return st_; }
   const long long tiles = (a.total_points + a.P - 1) / a.P;
   dim3 grid((unsigned)tiles, (unsigned)ncol);
   {

@@ -1,10 +1,14 @@
-// gather_mma2.cu -- second-generation fused gather + 3xTF32 tcgen05 kernel (forward and grad_input).
+// gather_mma2.cu -- fused gather + 3xTF32 tcgen05 kernel (forward and grad_input).
 //
-// Same contraction as forward_tc.cu (see there for the maths and the operand layout):
 //   out[p, n] = sum_f sum_k A_f[p, k] * Wpanel_f[n, k],   A_f = per-cell mean (forward, tf_conv3p_atrous.cpp:
-//   480-494) or weighted sum over the backward lists (grad_input, :682-692),
-// but the CUDA-core side of the fusion -- which bounded the first version (profiles/r1_summary.md: 4548 producer
-// cycles per (cell, sub-tile) group against 1572 cycles of MMA work) -- is reorganised:
+//   480-494) or weighted sum over the backward lists (grad_input, :682-692).
+// For T sub-tiles of 128 voxel-sorted points the (27*Csrc) x Nout contraction runs as T accumulators of 128 x Nout
+// fp32 in TMEM; K is walked as (kernel cell f, K batch, sub-tile t).  The aggregated operand A_f is never written
+// to HBM: producer warps gather neighbour rows with 16-byte loads (quarter-warp per point = one 128-byte row
+// segment per instruction), reduce them in registers, split the result into TF32 hi/lo parts and store them
+// straight into the 128B-swizzled K-major operand panels of a shared-memory ring; one thread issues tcgen05.mma
+// (kind::tf32, M=128, N=Nout, K=8): D += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (3xTF32, fp32 accumulation in TMEM).
+// The CUDA-core side of the fusion bounds the kernel (profiles/r1_summary.md), so it is organised around it:
 //
 //  * A PRE-PASS (k_group_items, one warp per 128-point sub-tile) turns the count table into, for every (sub-tile,
 //    cell) group, a list of 128 work items (list position, row, members), 1 KB per group, in scratch memory; the
@@ -24,6 +28,7 @@
 // allocator, NPW+2 = item-list loader.
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -553,28 +558,41 @@ struct G2Config {
 };
 
 // Csrc = contraction width per cell (Cin forward, Cout backward), Nout = output width.
+// Shared memory = operand ring (NAS stages of 32 KB: hi + lo panel of 128 rows x 32 channels) + weight units (hi or
+// lo half of one [Nout x 32] panel each) + tables.  Two 32-channel panels per group (NKC = 2: ids, weights and
+// predicates paid once per 256 bytes of row) when that leaves a ring of at least three stages, else one (e.g.
+// 256 -> 256, where a weight unit alone is 32 KB).  At least one weight unit beyond the 2 * NKC of the panel in use,
+// so the next panel's hi half is in flight while the tensor core still reads this one's lo half.
 static bool g2_config(int N, long long capacity, int Csrc, int Nout, G2Config* c) {
   if (N > 65535) return false;                // members per cell are packed in 24 bits, rows in 8
   if (capacity >= (1LL << 32)) return false;  // list positions are 32-bit
   if (Csrc % 32 || Nout % 16 || Csrc < 32 || Nout < 16 || Nout > 256) return false;
-  c->NKC = (Csrc % 64 == 0) ? 2 : 1;
-  c->nkb = Csrc / (32 * c->NKC);
   c->T = 512 / Nout >= 4 ? 4 : (512 / Nout);
   const size_t budget = 227 * 1024 - 2048;  // static shared memory (barriers, masks) + alignment slack
   const size_t unit = (size_t)Nout * PANEL_ROW_BYTES;
   const size_t tables = (size_t)c->T * 128 * 4 + (size_t)G2_NIS * 128 * 8;
-  c->NWU = 2 * c->NKC;
-  if (tables + c->NWU * unit > budget) return false;
-  size_t room = budget - tables - c->NWU * unit;
-  c->NAS = (int)(room / G2_A_STAGE);
-  if (c->NAS > G2_MAX_NAS) c->NAS = G2_MAX_NAS;
-  if (c->NAS < c->NKC + 1) return false;
-  room -= (size_t)c->NAS * G2_A_STAGE;
-  int extra = (int)(room / unit);
-  if (extra > 2) extra = 2;
-  c->NWU += extra;
-  c->smem = (size_t)c->NAS * G2_A_STAGE + (size_t)c->NWU * unit + tables;
-  return true;
+  for (int nkc = (Csrc % 64 == 0) ? 2 : 1; nkc >= 1; --nkc) {
+    c->NKC = nkc;
+    c->nkb = Csrc / (32 * nkc);
+    c->NWU = 2 * nkc;
+    if (tables + c->NWU * unit > budget) continue;
+    size_t room = budget - tables - c->NWU * unit;
+    c->NAS = (int)(room / G2_A_STAGE);
+    if (c->NAS > G2_MAX_NAS) c->NAS = G2_MAX_NAS;
+    if (c->NAS < nkc + 1) continue;
+    room -= (size_t)c->NAS * G2_A_STAGE;
+    int extra = (int)(room / unit);
+    if (extra == 0 && c->NAS >= nkc + 2 && room + G2_A_STAGE >= unit) {   // trade a ring stage for the spare unit
+      c->NAS -= 1;
+      room += G2_A_STAGE;
+      extra = (int)(room / unit);
+    }
+    if (extra > 2) extra = 2;
+    c->NWU += extra;
+    c->smem = (size_t)c->NAS * G2_A_STAGE + (size_t)c->NWU * unit + tables;
+    return true;
+  }
+  return false;
 }
 
 bool gather_mma2_supported(int N, long long capacity, int Csrc, int Nout) {
@@ -614,8 +632,12 @@ int launch_group_items(const conv3p_geom_t* g, const PlanView& v, bool backward_
       k_group_items<128><<<(unsigned)gi.subtiles, 128, 0, stream>>>(cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts,
                                                                     g->pair_capacity, g->N, gi.items, gi.nnz,
                                                                     gi.rowid, gi.mask, gi.counter);
-    else
+    else if (rows == 64)
       k_group_items<64><<<(unsigned)gi.subtiles, 64, 0, stream>>>(cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts,
+                                                                  g->pair_capacity, g->N, gi.items, gi.nnz, gi.rowid,
+                                                                  gi.mask, gi.counter);
+    else
+      k_group_items<32><<<(unsigned)gi.subtiles, 32, 0, stream>>>(cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts,
                                                                   g->pair_capacity, g->N, gi.items, gi.nnz, gi.rowid,
                                                                   gi.mask, gi.counter);
   }
@@ -647,13 +669,19 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
   a.total_points = pts; a.subtiles = subtiles;
   a.N = g->N; a.Csrc = Csrc; a.Nout = Nout;
   a.nkb = c.nkb; a.T = c.T; a.NAS = c.NAS; a.NWU = c.NWU;
-  a.debug = engine() >= 64 ? (engine() & ~(64 | 128 | 256)) : 0;
+  a.debug = engine_flag(32) ? 32 : 0;   // phase timers (tools/engine_timing.py)
   a.g_store = weighted ? g_store : nullptr;
-  a.res_big = 12; a.res_one = 4;   // 6 G and 2 G sub-tiles (tuned at 2048 sub-tiles; CONV3P_SCHED="big,one" overrides for sweeps)
-  if (const char* e = getenv("CONV3P_SCHED")) {
-    int x = 0, y = 0;
-    if (sscanf(e, "%d,%d", &x, &y) == 2 && x >= y && y >= 0) { a.res_big = x; a.res_one = y; }
-  }
+  // scheduler reserves: 6 G and 2 G sub-tiles (tuned at 2048 sub-tiles; CONV3P_SCHED="big,one", read once per
+  // process, overrides them for sweeps)
+  static const std::pair<int, int> sched = [] {
+    std::pair<int, int> r(12, 4);
+    if (const char* e = getenv("CONV3P_SCHED")) {
+      int x = 0, y = 0;
+      if (sscanf(e, "%d,%d", &x, &y) == 2 && x >= y && y >= 0) r = std::make_pair(x, y);
+    }
+    return r;
+  }();
+  a.res_big = sched.first; a.res_one = sched.second;
   a.src_stride = io.src_stride ? io.src_stride : Csrc;
   a.out_stride = io.out_stride ? io.out_stride : Nout;
   a.activation = io.activation;
@@ -661,12 +689,11 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
   if (a.src_stride % 4 || a.out_stride % 4 || reinterpret_cast<uintptr_t>(src) % 16 ||
       reinterpret_cast<uintptr_t>(out) % 16 || a.src_stride >= (1LL << 29))
     return CONV3P_ERR_UNSUPPORTED;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  (void)cudaGetLastError();
+  const int sms = sm_count();
   const long long tiles = subtiles < sms ? subtiles : sms;  // persistent CTAs, one per SM
   auto launch = [&](auto kern) -> int {
-    C3P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    const int st_ = ensure_dynamic_smem(kern, 227 * 1024 - 2048);   // once per (kernel, device)
+    if (st_) return st_;
     {
       LaunchTimer timer_(name, stream);
       kern<<<(unsigned)tiles, G2_THREADS, c.smem, stream>>>(a);

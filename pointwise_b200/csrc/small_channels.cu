@@ -440,20 +440,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_small_backward_filter2(const SFA
   }
 }
 
-__global__ void k_small_reduce(const float* __restrict__ partial, int S, int nW, float* __restrict__ out) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nW) return;
-  float s = 0.f;
-  for (int i = 0; i < S; ++i) s += partial[(size_t)i * nW + w];
-  out[w] = s;
-}
-
-static int sc_sms() {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  (void)cudaGetLastError();
-  return sms < 1 ? 148 : sms;
-}
+static int sc_sms() { return sm_count(); }
 
 // Measured on B200 (profiles/r1_summary.md): the warp-per-point gather-contract wins up to ~16 channels (2x at
 // ModelNet40 densities), the tile engine from 36->13 up; the private-copy grad_filter kernel wins whenever it fits.
@@ -466,29 +453,29 @@ static bool sc2_shape(int Csrc, int Nout) {
 // (13->36 grad_input at 16 x 4096 points: 0.39 ms against 0.41 ms)
 static bool sc2_gather_shape(int Csrc, int Nout) { return sc2_shape(Csrc, Nout) && Nout <= 32; }
 bool small_channels_supported(int Cin, int Cout) {
-  if (engine() & 1024) return Cin <= 16 && Cout <= 16;   // first version only (A/B timing)
+  if (engine_flag(1024)) return Cin <= 16 && Cout <= 16;   // first version only (A/B timing)
   return sc2_gather_shape(Cin, Cout) && sc2_gather_shape(Cout, Cin);   // forward and grad_input both
 }
 bool small_forward_supported(int Cin, int Cout) {
-  if (engine() & 1024) return Cin <= 16 && Cout <= 16;
+  if (engine_flag(1024)) return Cin <= 16 && Cout <= 16;
   return sc2_gather_shape(Cin, Cout);
 }
 bool small_backward_input_supported(int Cin, int Cout) {
-  if (engine() & 1024) return Cin <= 16 && Cout <= 16;
+  if (engine_flag(1024)) return Cin <= 16 && Cout <= 16;
   return sc2_gather_shape(Cout, Cin);
 }
 bool small_backward_filter_supported(int Cin, int Cout) {
-  if (!(engine() & 1024) && sc2_shape(Cin, Cout)) return true;
+  if (!(engine_flag(1024)) && sc2_shape(Cin, Cout)) return true;
   return Cin <= 40 && Cout <= 40 && (size_t)SC_WARPS * C3P_NCELL * Cin * Cout * 4 <= 96 * 1024;
 }
 
 static int launch_small_gc(SCArgs& a, const char* name, cudaStream_t stream) {
   if (a.total_points == 0) return CONV3P_OK;
-  if (sc2_gather_shape(a.Csrc, a.Nout) && !(engine() & 1024)) {   // engine bit 1024: first version (A/B timing)
+  if (sc2_gather_shape(a.Csrc, a.Nout) && !(engine_flag(1024))) {   // engine bit 1024: first version (A/B timing)
     const size_t smem2 = sizeof(float) * (((size_t)C3P_NCELL * a.Csrc * a.Nout + 3) / 4 * 4 +
                                           (size_t)SC_WARPS * sc2_warp_words(a.Csrc));
     if (smem2 > 40 * 1024)
-      C3P_CUDA(cudaFuncSetAttribute(k_small_gather_contract2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      { const int st_ = ensure_dynamic_smem(k_small_gather_contract2, smem2); if (st_) return st_; }
     long long grid2 = (long long)sc_sms() * (smem2 > 100 * 1024 ? 1 : (smem2 > 48 * 1024 ? 2 : 4));
     const long long need2 = (a.total_points + SC_WARPS - 1) / SC_WARPS;
     if (grid2 > need2) grid2 = need2;
@@ -501,7 +488,7 @@ static int launch_small_gc(SCArgs& a, const char* name, cudaStream_t stream) {
   }
   const size_t smem = sizeof(float) * C3P_NCELL * a.Csrc * a.Nout;
   if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default too)
-    C3P_CUDA(cudaFuncSetAttribute(k_small_gather_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int st_ = ensure_dynamic_smem(k_small_gather_contract, smem); if (st_) return st_; }
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
   long long grid = (long long)sc_sms() * per_sm;
   const long long need = (a.total_points + SC_WARPS - 1) / SC_WARPS;
@@ -557,7 +544,7 @@ int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, cons
   a.rows = v.bwd_row; a.weights = v.bwd_weight; a.sorted_xyzi = v.sorted_xyzi;
   a.partial = static_cast<float*>(scratch);
   a.total_points = pts; a.capacity = g->pair_capacity; a.N = g->N; a.Cin = Cin; a.Cout = Cout;
-  const bool v2 = sc2_shape(Cin, Cout) && !(engine() & 1024);   // engine bit 1024: first version (A/B timing)
+  const bool v2 = sc2_shape(Cin, Cout) && !(engine_flag(1024));   // engine bit 1024: first version (A/B timing)
   // second version: as many cells per pass as 8 private copies fit next to the aggregate areas with two CTAs per SM
   int cells_per_pass = C3P_NCELL;
   if (v2) {
@@ -571,9 +558,9 @@ int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, cons
                          : sizeof(float) * (size_t)SC_WARPS * nW;
   if (smem > 40 * 1024) {  // (static shared memory counts against the 48 KB default too)
     if (v2)
-      C3P_CUDA(cudaFuncSetAttribute(k_small_backward_filter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      { const int st_ = ensure_dynamic_smem(k_small_backward_filter2, smem); if (st_) return st_; }
     else
-      C3P_CUDA(cudaFuncSetAttribute(k_small_backward_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      { const int st_ = ensure_dynamic_smem(k_small_backward_filter, smem); if (st_) return st_; }
   }
   const int per_sm = smem > 113 * 1024 ? 1 : 2;
   int sms = sc_sms();
@@ -589,12 +576,7 @@ int launch_backward_filter_small(const conv3p_geom_t* g, const PlanView& v, cons
       k_small_backward_filter<<<(unsigned)grid, SC_THREADS, smem, stream>>>(a);
   }
   C3P_LAUNCH_CHECK("k_small_backward_filter");
-  {
-    LaunchTimer timer_("k_reduce_partials", stream);
-    k_small_reduce<<<(nW + 255) / 256, 256, 0, stream>>>(a.partial, (int)grid, nW, grad_filter);
-  }
-  C3P_LAUNCH_CHECK("k_reduce_partials");
-  return CONV3P_OK;
+  return launch_reduce_partials(a.partial, (int)grid, nW, grad_filter, v.header, stream);
 }
 
 }  // namespace c3p

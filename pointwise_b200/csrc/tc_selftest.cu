@@ -179,7 +179,7 @@ extern "C" int conv3p_selftest_tc_mn(const float* A, const float* B, float* D, i
   using namespace c3p;
   if (N < 32 || N > 256 || N % 32 || K < 8 || K > 64 || K % 8) return CONV3P_ERR_INVALID_ARGUMENT;
   const size_t smem = 2 * (size_t)(4 + N / 32) * K * tc::PANEL_ROW_BYTES;
-  C3P_CUDA(cudaFuncSetAttribute(k_tc_selftest_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int st_ = ensure_dynamic_smem(k_tc_selftest_mn, smem); if (st_) return st_; }
   k_tc_selftest_mn<<<1, 128, smem, stream>>>(A, B, D, N, K, split);
   C3P_LAUNCH_CHECK("k_tc_selftest_mn");
   return CONV3P_OK;
@@ -190,7 +190,7 @@ extern "C" int conv3p_selftest_tc(const float* A, const float* B, float* D, int 
   using namespace c3p;
   if (N < 16 || N > 256 || N % 16 || K < 32 || K % 32) return CONV3P_ERR_INVALID_ARGUMENT;
   const size_t smem = 2 * 128 * tc::PANEL_ROW_BYTES + 2 * (size_t)N * tc::PANEL_ROW_BYTES + 1024;
-  C3P_CUDA(cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int st_ = ensure_dynamic_smem(k_tc_selftest, smem); if (st_) return st_; }
   k_tc_selftest<<<1, 128, smem, stream>>>(A, B, D, N, K, split);
   C3P_LAUNCH_CHECK("k_tc_selftest");
   return CONV3P_OK;

@@ -41,6 +41,31 @@ def allreduce_grad_filter(grad_filter: torch.Tensor, group=None, async_op: bool 
     return dist.all_reduce(grad_filter, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+_comm_streams = {}
+
+
+def allreduce_grad_filter_overlapped(grad_filter: torch.Tensor, group=None):
+    """The same all-reduce on a dedicated communication stream, ordered after everything already enqueued on the
+    current stream.  Returns a CUDA event (or None when there is nothing to reduce): whoever consumes
+    ``grad_filter`` next -- the optimizer step -- makes its stream wait for it.  Kernels enqueued on the current
+    stream in the meantime (the next batch's voxel sort and neighbour search do not depend on the gradient) overlap
+    the collective, so at weak scaling the 885 KB message and its launch latency leave the critical path."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    dev = grad_filter.device
+    key = dev.index
+    if key not in _comm_streams:
+        _comm_streams[key] = torch.cuda.Stream(dev)
+    comm = _comm_streams[key]
+    comm.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(comm):
+        dist.all_reduce(grad_filter, op=dist.ReduceOp.SUM, group=group)
+        done = torch.cuda.Event()
+        done.record(comm)
+    grad_filter.record_stream(comm)
+    return done
+
+
 def conv3p_grad_sharded(grad_from_next, points, input, filter, stride, voxel_size, group=None):
     """Conv3pGrad on this rank's shard followed by the all-reduce: every rank returns its shard's
     grad_input and the GLOBAL grad_filter."""

@@ -69,8 +69,9 @@ class HostConv3p:
             s["copied"].record(self.s_h2d)
         with torch.cuda.stream(self.s_compute):
             self.s_compute.wait_event(s["copied"])
+            # overflow check deferred to fetch(): nothing synchronises while the step is enqueued
             plan = NeighborPlan(s["points"], self.stride, self.voxel, capacity=self.capacity,
-                                check=self.capacity is None)
+                                check=True if self.capacity is None else "deferred")
             out = conv3p_forward(plan, s["input"], s["filter"])
             plan.prefetch_backward()
             gi, gf = conv3p_backward(plan, s["grad_out"], s["input"], s["filter"])
@@ -93,7 +94,9 @@ class HostConv3p:
         """Blocks until the step's results are in host memory -> (output, grad_input, grad_filter) pinned."""
         s = self.slots[ticket % self.depth]
         s["fetched"].synchronize()
-        s["keep"] = None
+        keep, s["keep"] = s["keep"], None
+        if keep is not None:
+            keep[0].verify(block=True)   # raises ERR_PAIR_OVERFLOW if this step's neighbour lists were incomplete
         return s["h_out"], s["h_gi"], s["h_gf"]
 
     def last_event(self):

@@ -26,6 +26,11 @@ import torch.nn.functional as F
 from .ops import NeighborPlan, conv3p, conv3p_forward, parse_stride, parse_voxel
 
 
+# False: every conv3p call builds its own plan (what a literal drop-in call without `plan=` does) -- bench.py's A/B of
+# plan sharing.  Results are identical either way.
+SHARE_PLANS = True
+
+
 class PlanCache:
     """Neighbour plans of ONE batch of points, keyed by stride (voxel size fixed)."""
 
@@ -36,6 +41,8 @@ class PlanCache:
 
     def get(self, stride) -> NeighborPlan:
         s = parse_stride(stride)
+        if not SHARE_PLANS:
+            return NeighborPlan(self.points, s, self.voxel)
         if s not in self.plans:
             self.plans[s] = NeighborPlan(self.points, s, self.voxel)
         return self.plans[s]

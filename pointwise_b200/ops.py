@@ -119,6 +119,26 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
 # neighbour plan
 # --------------------------------------------------------------------------------------------------
 _capacity_hint: dict = {}
+_pending_checks: list = []     # plans whose deferred overflow check has not been read yet (weak references)
+
+
+def _poll_pending_checks() -> None:
+    """Non-blocking: reads the overflow flag of earlier plans whose header copy has arrived; raises if one of them
+    overflowed (its outputs were NaN-poisoned on the device)."""
+    alive = []
+    err = None
+    for ref in _pending_checks:
+        plan = ref()
+        if plan is None or plan._stats_event is None:
+            continue
+        try:
+            if not plan.verify(block=False):
+                alive.append(ref)
+        except _lib.Conv3pError as e:      # report the first, keep draining the list
+            err = err or e
+    _pending_checks[:] = alive
+    if err is not None:
+        raise err
 
 
 class NeighborPlan:
@@ -130,14 +150,24 @@ class NeighborPlan:
     by the forward and backward pass (the reference rebuilds its grid twice per layer per step,
     tf_conv3p_atrous.cpp:463, 629).
 
-    ``capacity`` bounds the total number of (point, neighbour) pairs.  ``None`` sizes it
-    automatically: a remembered estimate is tried first and verified with one 64-byte device->host
-    read (``check=True``); with ``check=False`` nothing is read back and an overflow poisons the
-    affected outputs with NaN instead of raising.
+    ``capacity`` bounds the total number of (point, neighbour) pairs (data dependent).  ``capacity=None`` sizes it
+    automatically and WITHOUT a host synchronisation in steady state ("no host synchronisation inside
+    forward/backward"; the reference's GPU op blocks twice per call, tf_conv3p_atrous.cu:577, 586):
+
+    * the first plan of a (B, N, stride, voxel) shape is built with a synchronous check (one 128-byte read-back,
+      rebuilt larger if the guess was too small) and leaves a grow-only estimate with 25 % head-room;
+    * every later plan of that shape uses the estimate and only ENQUEUES a copy of the plan's counters into pinned
+      host memory.  The copy is looked at later -- when the backward pass starts, when the next plan is built, or
+      on ``verify()`` / ``stats`` -- by which time it has long arrived.  Should a batch ever exceed the estimate,
+      the affected outputs were NaN-poisoned on the device (never silently wrong), the estimate is raised and a
+      ``Conv3pError(ERR_PAIR_OVERFLOW)`` is raised at that point: rerun the step.
+
+    ``check="sync"`` always checks synchronously, ``check="deferred"`` never does (also with an explicit
+    ``capacity``, which is otherwise checked synchronously); ``check=False`` never reads anything back (poison only).
     """
 
     def __init__(self, points: torch.Tensor, stride, voxel_size, capacity: Optional[int] = None,
-                 check: bool = True):
+                 check=True):
         points = _check_cuda_f32(points, "points")
         if points.dim() != 3 or points.shape[2] != 3:
             raise ValueError("Conv3p expects (batch_size, num_points, 3) points shape")
@@ -147,10 +177,17 @@ class NeighborPlan:
         self.B, self.N = int(points.shape[0]), int(points.shape[1])
         self.device = points.device
         self.has_backward = False
-        self.stats = None
+        self._stats = None
+        self._stats_event = None
+        self._stats_host = None
         L = _lib.lib()
-        key = (self.B, self.N, self.stride, self.voxel_size)
+        self._key = key = (self.B, self.N, self.stride, self.voxel_size)
         pts = self.B * self.N
+        if check:
+            _poll_pending_checks()
+        learned = capacity is None and key in _capacity_hint
+        sync_check = check == "sync" or (check is True and not learned)
+        self._auto = capacity is None
         cap = int(capacity) if capacity is not None else _capacity_hint.get(key, max(1024, 48 * pts))
         while True:
             self.capacity = cap
@@ -162,7 +199,7 @@ class NeighborPlan:
             with torch.cuda.device(self.device):
                 _lib.check(L.conv3p_plan_build_f32(self.geom, _ptr(points), _ptr(self.buffer), nbytes,
                                                    _stream_ptr(self.device)))
-            if not check:
+            if not sync_check:
                 break
             st = self.read_stats()
             if not st.overflow:
@@ -171,17 +208,68 @@ class NeighborPlan:
                 raise _lib.Conv3pError(_lib.ERR_PAIR_OVERFLOW,
                                        f"pair capacity {cap} too small, {st.total_pairs} pairs needed")
             cap = int(st.total_pairs * 1.125) + 1024
-        if capacity is None and check:
-            # grow-only estimate for the next batch of this shape
-            want = int(self.stats.total_pairs * 1.25) + 1024
-            _capacity_hint[key] = max(_capacity_hint.get(key, 0), want)
+        if self._auto and sync_check:
+            self._learn(self._stats.total_pairs)
         lay = _lib.PlanLayout()
         _lib.check(L.conv3p_plan_layout(self.geom, lay))
         self.layout = lay
+        if check and not sync_check and pts > 0:     # check == "deferred", or True with a learned estimate
+            self._enqueue_header_copy()
         # the forward lists are complete at this point of the stream: a later prefetch_backward() starts from here
         self._searched = torch.cuda.Event()
         self._searched.record(torch.cuda.current_stream(self.device))
         self._bwd_ready = None
+
+    def _learn(self, total_pairs: int) -> None:
+        """grow-only capacity estimate for the next batch of this shape"""
+        want = int(total_pairs * 1.25) + 1024
+        _capacity_hint[self._key] = max(_capacity_hint.get(self._key, 0), want)
+
+    # ---- deferred overflow check -----------------------------------------------------------------
+    def _enqueue_header_copy(self) -> None:
+        import weakref
+        self._stats_host = torch.empty(16, dtype=torch.int64).pin_memory()
+        hdr = self.buffer[self.layout.header:self.layout.header + 128].view(torch.int64)
+        self._stats_host.copy_(hdr, non_blocking=True)
+        self._stats_event = torch.cuda.Event()
+        self._stats_event.record(torch.cuda.current_stream(self.device))
+        _pending_checks.append(weakref.ref(self))
+
+    def verify(self, block: bool = True) -> bool:
+        """Looks at the deferred copy of the plan's counters.  Returns False when it has not arrived yet and
+        ``block`` is False; raises Conv3pError(ERR_PAIR_OVERFLOW) if the lists were incomplete."""
+        ev = self._stats_event
+        if ev is None:
+            return True
+        if block:
+            ev.synchronize()          # waits for the plan build only (recorded right after it), not for the stream
+        elif not ev.query():
+            return False
+        self._stats_event = None
+        h = self._stats_host.tolist()
+        st = _lib.PlanStats()
+        st.total_pairs, st.backward_pairs = int(h[0]), int(h[2])
+        st.overflow = 1 if (h[1] != 0 or h[0] > self.capacity) else 0
+        st.has_backward = 1 if h[3] != 0 else 0
+        self._stats = st
+        if self._auto:
+            self._learn(st.total_pairs)
+        if st.overflow:
+            raise _lib.Conv3pError(
+                _lib.ERR_PAIR_OVERFLOW,
+                f"pair capacity {self.capacity} was too small for this batch ({st.total_pairs} pairs): the affected "
+                "outputs were NaN-poisoned; the capacity estimate has been raised, rerun the step")
+        return True
+
+    @property
+    def stats(self):
+        """Counters of the plan (reads them back on first use)."""
+        if self._stats is None:
+            if self._stats_event is not None:
+                self.verify(block=True)
+            else:
+                self.read_stats()
+        return self._stats
 
     # ---- stats / views -------------------------------------------------------------------------
     def read_stats(self):
@@ -190,7 +278,7 @@ class NeighborPlan:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().conv3p_plan_stats(self.geom, _ptr(self.buffer), st,
                                                     _stream_ptr(self.device)))
-        self.stats = st
+        self._stats = st
         return st
 
     def _view(self, offset: int, count: int, dtype: torch.dtype) -> torch.Tensor:
@@ -369,6 +457,7 @@ def conv3p_backward(plan: NeighborPlan, grad_output: torch.Tensor, input: torch.
         raise ValueError("backprop grad tensor has wrong size for dim 1")
     if grad_output.shape[2] != Cout:
         raise ValueError("backprop grad tensor has wrong size for dim 2")
+    plan.verify(block=True)      # deferred overflow check of the plan (its copy arrived long ago: no stream sync)
     plan.ensure_backward()
     L = _lib.lib()
     gi = torch.empty((plan.B, plan.N, Cin), dtype=torch.float32, device=plan.device) \
@@ -380,7 +469,12 @@ def conv3p_backward(plan: NeighborPlan, grad_output: torch.Tensor, input: torch.
         nshared = L.conv3p_backward_scratch_bytes(plan.geom, Cin, Cout)
         if nshared - nscratch <= G_STORE_LIMIT_BYTES:
             nscratch = nshared
-    scratch = torch.empty(nscratch, dtype=torch.uint8, device=plan.device)
+    try:
+        scratch = torch.empty(nscratch, dtype=torch.uint8, device=plan.device)
+    except torch.OutOfMemoryError:
+        # no room for the G store: the smaller scratch gives identical results (each gradient kernel gathers)
+        nscratch = L.conv3p_scratch_bytes(plan.geom, Cin, Cout)
+        scratch = torch.empty(nscratch, dtype=torch.uint8, device=plan.device)
     with torch.cuda.device(plan.device):
         _lib.check(L.conv3p_backward_f32(plan.geom, _ptr(plan.buffer), _ptr(grad_output), _ptr(input),
                                          _ptr(kernel), Cin, Cout, _ptr(gi), _ptr(gf), _ptr(scratch),
@@ -456,11 +550,11 @@ def conv3p_grad(grad_from_next, points, input, filter, stride, voxel_size,
 
 def set_engine(engine: str = "auto") -> str:
     """Selects the contraction engine: "auto" (tensor cores where the shape allows, else SIMT),
-    "simt" (fp32 CUDA cores only), "tc", or "tile" (the generic fp32 tile kernels only).  Returns the previous
-    setting."""
+    "simt" (fp32 CUDA cores only: warp-per-point or tile kernels by channel count), "tc", or "tile" (the generic fp32
+    tile kernels only, no tensor cores).  Returns the previous setting."""
     names = ["auto", "simt", "tc", "tile"]
     prev = _lib.lib().conv3p_set_engine(names.index(engine))
-    return names[prev]
+    return names[prev & 7] if (prev & 7) < len(names) else "auto"   # higher bits are ablation flags
 
 
 def launch_count(reset: bool = False) -> int:

@@ -79,3 +79,51 @@ def test_sharded_backward_equals_full_batch_gloo():
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(r[1] for r in results), "shard results differ from the full-batch oracle"
     assert all(r[2] for r in results), "ranks disagree on the reduced grad_filter"
+
+
+# ---- the same gate on real GPUs over NCCL ----------------------------------------------------
+def _nccl_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from pointwise_b200.distributed import conv3p_grad_sharded
+        from pointwise_b200 import conv3p_grad
+        B, N, Cin, Cout, stride, V = 6, 1024, 64, 128, (1, 1, 1), 0.1
+        pr = make_problem(B, N, Cin, Cout, "room", seed=5)
+        full = {k: torch.from_numpy(v).to(dev) for k, v in pr.items()}
+        mine = {k: shard_batch(full[k], rank, world).contiguous() for k in ("points", "input", "grad_out")}
+        gi, gf = conv3p_grad_sharded(mine["grad_out"], mine["points"], mine["input"], full["filter"], stride, V)
+        gi_full, gf_full = conv3p_grad(full["grad_out"], full["points"], full["input"], full["filter"], stride, V)
+        lo, hi = shard_range(B, rank, world)
+        gathered = [torch.empty_like(gf) for _ in range(world)]
+        dist.all_gather(gathered, gf)
+        same = all(torch.equal(gathered[0], g) for g in gathered)
+        scale = float(gf_full.abs().max())
+        ok = torch.equal(gi, gi_full[lo:hi]) and float((gf - gf_full).abs().max()) <= 2e-5 * scale
+        q.put((rank, bool(ok), bool(same)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_backward_equals_full_batch_nccl():
+    """Two ranks over NCCL: identical grad_filter on both, equal to the single-GPU result on the concatenated
+    batch within fp32 summation tolerance; grad_input of a shard bit-identical to the full-batch rows."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in results), "shard results differ from the full-batch result"
+    assert all(r[2] for r in results), "ranks disagree on the reduced grad_filter"

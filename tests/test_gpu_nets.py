@@ -33,6 +33,48 @@ def test_segmentation_net_matches_oracle_chain(port):
     np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5)
 
 
+def test_classification_net_matches_oracle_chain(port):
+    """pointcnn2_acsd.py:48-75 evaluated with the CPU oracle (Conv3p layers), numpy SELU and numpy dense layers."""
+    from pointwise_b200.nets import PointConvNetCls
+    torch.manual_seed(0)
+    B, N, C, K = 4, 1024, 3, 40
+    pts = make_points(B, N, "sphere", seed=7)
+    net = PointConvNetCls(K, N, C).cuda()
+    got = net.model(torch.from_numpy(pts).cuda(), torch.from_numpy(pts.copy()).cuda(), is_training=False)
+    got = got.detach().cpu().numpy()
+    W = [w.detach().cpu().numpy() for w in net.filters]
+    x, outs = pts, []
+    for i in range(4):                                                  # :48-67, strides 1..4
+        x = selu_np(port.forward(pts, x, W[i], i + 1, 0.1))
+        outs.append(x)
+    feat = np.concatenate(outs, axis=2).reshape(B, -1).astype(np.float64)      # :69-70
+    w1, b1 = net.fc1.weight.detach().cpu().numpy().astype(np.float64), net.fc1.bias.detach().cpu().numpy()
+    w2, b2 = net.fc2.weight.detach().cpu().numpy().astype(np.float64), net.fc2.bias.detach().cpu().numpy()
+    h = selu_np(feat @ w1.T + b1).astype(np.float64)                   # :71 (no dropout at inference, :73)
+    want = selu_np(h @ w2.T + b2)                                       # :75
+    np.testing.assert_allclose(got, want, rtol=2e-3, atol=2e-4)       # torch's dense layers run in TF32-free fp32
+
+
+def test_selu_gradient_at_exactly_zero_follows_the_reference():
+    """selu.py:25 takes the linear branch for x >= 0, so at a pre-activation of exactly 0 (all neighbour rows zero:
+    padded rows, zero features) the derivative is `scale`, not scale * alpha."""
+    from pointwise_b200 import conv3p
+    from pointwise_b200.synth import make_problem
+    scale = 1.0507009873554804934193349852946
+    pr = make_problem(1, 300, 9, 9, "room", seed=19)
+    P = torch.from_numpy(pr["points"]).cuda()
+    x = torch.zeros(1, 300, 9, device="cuda", requires_grad=True)           # y = selu(0) = 0 everywhere
+    w = torch.from_numpy(pr["filter"]).cuda().requires_grad_()
+    g = torch.from_numpy(pr["grad_out"]).cuda()
+    y = conv3p(P, x, w, [1, 1, 1], [0.1], activation="selu")
+    assert float(y.abs().max()) == 0.0
+    y.backward(g)
+    x2 = torch.zeros(1, 300, 9, device="cuda", requires_grad=True)
+    y2 = conv3p(P, x2, w.detach(), [1, 1, 1], [0.1])
+    y2.backward(g * scale)
+    assert torch.equal(x.grad, x2.grad)
+
+
 def test_classification_net_trains():
     """pointcnn2_acsd.py:37-89 at the ModelNet40 shape: loss decreases, gradients reach every filter, one plan
     per stride."""

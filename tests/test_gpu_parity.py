@@ -154,6 +154,17 @@ FEATURE_CASES = [
     (1, 4096, 64, 64, (2, 2, 2), "room", None),     # BASELINE sweep: C=64, dilated
     (1, 1024, 256, 256, (1, 1, 1), "room", None),   # BASELINE sweep: C=256
     (1, 1, 4, 4, (1, 1, 1), "cube", None),
+    # BASELINE configs[1] at full size: the ModelNet40 classification layers, B=32 x 1024 (pointcnn2_acsd.py:48-67)
+    (32, 1024, 3, 9, (1, 1, 1), "sphere", None),
+    (32, 1024, 9, 9, (2, 2, 2), "sphere", None),
+    (32, 1024, 9, 9, (3, 3, 3), "sphere", None),
+    (32, 1024, 9, 9, (4, 4, 4), "sphere", None),
+    # BASELINE configs[2] at full size: the S3DIS segmentation layers, B=16 x 4096 (pointcnn_scene_seg_acsd.py:51-57)
+    (16, 4096, 9, 9, (1, 1, 1), "room", None),
+    (16, 4096, 9, 9, (2, 2, 2), "room", None),
+    (16, 4096, 9, 9, (3, 3, 3), "room", None),
+    (16, 4096, 9, 9, (4, 4, 4), "room", None),
+    (16, 4096, 36, 13, (1, 1, 1), "room", None),
 ]
 
 
@@ -305,6 +316,28 @@ def test_full_size_properties():
     assert abs(lhs - (gf.double() * W.double()).sum()) <= 1e-3 * abs(lhs) + 1.0
 
 
+def test_full_size_three_clouds_against_oracle(port):
+    """The benchmarked configuration itself (clouds of 4096 points, 64->128): three clouds of a 16-cloud batch
+    compared with the oracle -- rows of the full-batch output / grad_input, and grad_filter of a call on exactly
+    those clouds (clouds are independent: tf_conv3p_atrous.cpp:456, 622)."""
+    from pointwise_b200 import NeighborPlan, conv3p_backward, conv3p_forward
+    B, N, Cin, Cout = 16, 4096, 64, 128
+    pr = make_problem(B, N, Cin, Cout, "room", seed=0)
+    P, X, W, G = (dev(pr[k]) for k in ("points", "input", "filter", "grad_out"))
+    plan = NeighborPlan(P, 1, V)
+    y = conv3p_forward(plan, X, W)
+    gi, _ = conv3p_backward(plan, G, X, W)
+    idx = [0, 7, 15]
+    sub = {k: (v[idx] if k != "filter" else v) for k, v in pr.items()}
+    o32, o64, oabs = port.forward(sub["points"], sub["input"], sub["filter"], 1, V, with64=True)
+    r = port.backward(sub["grad_out"], sub["points"], sub["input"], sub["filter"], 1, V, with64=True)
+    assert_close_scaled(y[idx].cpu().numpy(), o64, oabs, RTOL, ATOL, "forward (full-size batch)")
+    assert_close_scaled(gi[idx].cpu().numpy(), r[2], r[3], RTOL, ATOL, "grad_input (full-size batch)")
+    plan3 = NeighborPlan(dev(sub["points"]), 1, V)
+    _, gf3 = conv3p_backward(plan3, dev(sub["grad_out"]), dev(sub["input"]), W)
+    assert_close_scaled(gf3.cpu().numpy(), r[4], r[5], RTOL, ATOL, "grad_filter (three full-size clouds)")
+
+
 def test_c_abi_one_shot_and_host_calls(port):
     """The reference-facing C entry points: device one-shot calls and host-buffer calls."""
     import ctypes as C
@@ -381,18 +414,30 @@ def test_c_abi_one_shot_backward_with_and_without_shared_gather(port):
     assert_close_scaled(res[1][1], r[4], r[5], RTOL, ATOL, "one-shot grad_filter")
 
 
-@pytest.mark.parametrize("Cin,Cout", [(64, 128), (32, 64), (64, 64), (32, 128), (128, 32), (96, 48), (128, 128)])
+TC_SHAPES = [(64, 128), (32, 64), (64, 64), (32, 128), (128, 32), (96, 48), (128, 128), (256, 256), (64, 256),
+             (32, 32), (256, 64)]
+
+
+def tc_filter_shape(Cin, Cout):
+    """Shapes whose weight gradient runs on tensor cores (backward_filter2.cu: M = 128 lanes = Cout block or stacked
+    cells, N = Cin in 32-wide panels)."""
+    return Cout in (32, 64, 128, 256) and Cin % 32 == 0 and 32 <= Cin <= 256
+
+
+@pytest.mark.parametrize("Cin,Cout", TC_SHAPES)
 def test_tensor_core_engine_matches_oracle_and_simt(port, Cin, Cout):
-    """The tcgen05 3xTF32 engine and the fp32 SIMT engine both sit inside the same tolerance
-    (forward and input gradient)."""
+    """The tcgen05 3xTF32 engine and the fp32 SIMT engine both sit inside the same tolerance (forward, input
+    gradient and weight gradient), and the tensor-core engine is really the one selected."""
     from pointwise_b200 import NeighborPlan, conv3p_backward, conv3p_forward, set_engine
     B, N, stride = 2, 1100, (1, 1, 1)          # 2200 points: several tiles, a ragged tail
+    if Cin * Cout >= 256 * 256:
+        N = 500                                # keeps the CPU checker in seconds
     pr = make_problem(B, N, Cin, Cout, "room", seed=12, quantise=0.05 if Cin == 64 and Cout == 64 else None)
     plan = NeighborPlan(dev(pr["points"]), stride, V)
     o32, o64, oabs = port.forward(pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
     r = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
     outs, gins, gfs = {}, {}, {}
-    for eng in ("simt", "tc"):
+    for eng in ("simt", "tc", "tile"):
         prev = set_engine(eng)
         try:
             outs[eng] = conv3p_forward(plan, dev(pr["input"]), dev(pr["filter"])).cpu().numpy()
@@ -404,10 +449,13 @@ def test_tensor_core_engine_matches_oracle_and_simt(port, Cin, Cout):
         assert assert_close_scaled(gins[eng], r[2], r[3], RTOL, ATOL, f"grad_input[{eng}]") < RTOL
         assert assert_close_scaled(gfs[eng], r[4], r[5], RTOL, ATOL, f"grad_filter[{eng}]") < RTOL
     assert not np.array_equal(outs["simt"], outs["tc"]), "tensor-core engine was not selected (forward)"
+    assert not np.array_equal(outs["tile"], outs["tc"]), "engine 'tile' must not use tensor cores"
     if Cout % 32 == 0:
         assert not np.array_equal(gins["simt"], gins["tc"]), "tensor-core engine was not selected (grad_input)"
-    if Cout == 128 and Cin <= 64:
+    if tc_filter_shape(Cin, Cout):
         assert not np.array_equal(gfs["simt"], gfs["tc"]), "tensor-core engine was not selected (grad_filter)"
+    else:
+        assert np.array_equal(gfs["simt"], gfs["tc"])
 
 
 def test_host_pipeline_matches_direct_calls():
@@ -482,19 +530,21 @@ def test_small_channel_engine_and_tile_engine_match_oracle(port, Cin, Cout, stri
     assert res["simt"].shape == res["tile"].shape
 
 
-@pytest.mark.parametrize("B,N,stride,dist,q", [(3, 1500, 1, "room", 0.0), (2, 2048, 2, "room", 0.05),
-                                               (4, 700, 1, "sphere", 0.0), (1, 129, 3, "cube", 0.0)])
-def test_shared_gather_of_the_two_gradients_is_bit_identical(B, N, stride, dist, q):
+@pytest.mark.parametrize("B,N,stride,dist,q,Cin,Cout", [
+    (3, 1500, 1, "room", 0.0, 64, 128), (2, 2048, 2, "room", 0.05, 64, 128), (4, 700, 1, "sphere", 0.0, 64, 128),
+    (1, 129, 3, "cube", 0.0, 64, 128), (2, 900, 1, "room", 0.0, 64, 64), (2, 600, 1, "room", 0.05, 32, 32),
+    (1, 700, 1, "room", 0.0, 256, 256), (2, 800, 2, "room", 0.0, 128, 64)])
+def test_shared_gather_of_the_two_gradients_is_bit_identical(B, N, stride, dist, q, Cin, Cout):
     """With both gradients requested the grad_input kernel leaves its per-(point, cell) aggregates of grad_output in
     the G store and the grad_filter kernel reads them back instead of walking the backward lists again: same
     members, same order of additions -> bit-identical to the un-shared kernels (engine bit 256) and to a call that
     asks for grad_filter alone."""
     from pointwise_b200 import NeighborPlan, _lib, conv3p_backward
-    Cin, Cout = 64, 128
     pr = make_problem(B, N, Cin, Cout, dist, seed=77, quantise=q or None)
     plan = NeighborPlan(dev(pr["points"]), (stride,) * 3, V).ensure_backward()
     g, x, w = dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"])
     L = _lib.lib()
+    assert L.conv3p_backward_scratch_bytes(plan.geom, Cin, Cout) > L.conv3p_scratch_bytes(plan.geom, Cin, Cout)
     gi_s, gf_s = conv3p_backward(plan, g, x, w)
     prev = L.conv3p_set_engine(256)
     try:
@@ -507,3 +557,56 @@ def test_shared_gather_of_the_two_gradients_is_bit_identical(B, N, stride, dist,
     assert torch.equal(gf_s, gf_u)
     assert torch.equal(gf_s, gf_only)
     assert float(gf_s.abs().max()) > 0
+
+
+def test_overflow_poisons_grad_filter_too():
+    """An unchecked plan whose pair capacity is too small: every affected output is NaN, including the weight
+    gradient (it would otherwise silently miss the overflowed points' terms), on every engine."""
+    from pointwise_b200 import NeighborPlan, conv3p_backward, set_engine
+    for Cin, Cout, eng in [(4, 4, "simt"), (9, 9, "simt"), (9, 9, "tile"), (64, 128, "tc"), (64, 64, "tc")]:
+        pr = make_problem(1, 512, Cin, Cout, "sphere", seed=1)
+        plan = NeighborPlan(dev(pr["points"]), 1, V, capacity=600, check=False)
+        prev = set_engine(eng)
+        try:
+            gi, gf = conv3p_backward(plan, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]))
+        finally:
+            set_engine(prev)
+        assert torch.isnan(gf).all(), (Cin, Cout, eng)
+        assert torch.isnan(gi).any() and not torch.isnan(gi).all()
+
+
+def test_deferred_overflow_check_has_no_sync_in_steady_state_and_reports_late():
+    """Second plan of a shape: built from the learned estimate, counters copied asynchronously; verify() / stats read
+    them later.  An explicit, too small capacity with check="deferred" raises at verify(), not at construction."""
+    from pointwise_b200 import Conv3pError, NeighborPlan
+    pts = dev(make_points(2, 640, "sphere", seed=21))
+    first = NeighborPlan(pts, 1, V)                 # learning build: synchronous
+    assert first._stats_event is None and first.stats.total_pairs > 0
+    second = NeighborPlan(pts, 1, V)                # steady state: deferred
+    assert second._stats_event is not None and second._stats is None
+    assert second.verify(block=True) and second.stats.total_pairs == first.stats.total_pairs
+    assert torch.equal(second.count_table, first.count_table)
+    late = NeighborPlan(pts, 1, V, capacity=700, check="deferred")
+    with pytest.raises(Conv3pError, match="capacity"):
+        late.verify(block=True)
+
+
+def test_backward_without_lists_is_an_error_status():
+    """C ABI: conv3p_backward_f32 on a plan whose backward lists were never built -> CONV3P_ERR_NO_BACKWARD_LISTS."""
+    from pointwise_b200 import _lib
+    L = _lib.lib()
+    B, N, Cin, Cout = 1, 300, 4, 4
+    pr = make_problem(B, N, Cin, Cout, "cube", seed=3)
+    g = _lib.make_geom(B, N, (1, 1, 1), V, 64 * N)
+    plan = torch.empty(L.conv3p_plan_bytes(g), dtype=torch.uint8, device="cuda")
+    scratch = torch.empty(L.conv3p_scratch_bytes(g, Cin, Cout), dtype=torch.uint8, device="cuda")
+    P, X, W, G = (dev(pr[k]) for k in ("points", "input", "filter", "grad_out"))
+    gi, gf = torch.empty_like(X), torch.empty_like(W)
+    _lib.check(L.conv3p_plan_build_f32(g, P.data_ptr(), plan.data_ptr(), plan.numel(), None))
+    args = (g, plan.data_ptr(), G.data_ptr(), X.data_ptr(), W.data_ptr(), Cin, Cout, gi.data_ptr(), gf.data_ptr(),
+            scratch.data_ptr(), scratch.numel(), None)
+    assert L.conv3p_backward_f32(*args) == _lib.ERR_NO_BACKWARD_LISTS
+    _lib.check(L.conv3p_plan_build_backward(g, P.data_ptr(), plan.data_ptr(), plan.numel(), None))
+    assert L.conv3p_backward_f32(*args) == _lib.OK
+    torch.cuda.synchronize()
+    assert torch.isfinite(gi).all() and torch.isfinite(gf).all()
