@@ -107,6 +107,13 @@ int conv3p_plan_build_backward(const conv3p_geom_t* geom, const float* points, v
 int conv3p_plan_stats(const conv3p_geom_t* geom, const void* plan, conv3p_plan_stats_t* out /* host */,
                       conv3p_stream_t stream);
 
+/* Asynchronous variant: enqueues a one-warp kernel that stores the plan's 16 counters (int64: [0] total pairs,
+ * [1] overflow flag, [2] backward pairs, [3] has_backward) into `host_mapped16`, which must be page-locked host
+ * memory that the device can address (cudaHostAlloc / cudaMallocHost under unified addressing).  No copy engine, no
+ * synchronisation: the caller waits on an event recorded after this call before reading the values. */
+int conv3p_plan_publish_stats(const conv3p_geom_t* geom, const void* plan, long long* host_mapped16,
+                              conv3p_stream_t stream);
+
 /* ---- the operator on a built plan ------------------------------------------------------------- */
 
 size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout);

@@ -22,7 +22,7 @@ ERR_NO_BACKWARD_LISTS = 6
 # every symbol include/conv3p_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "conv3p_plan_bytes", "conv3p_plan_layout", "conv3p_plan_build_f32", "conv3p_plan_build_backward",
-    "conv3p_plan_stats", "conv3p_scratch_bytes", "conv3p_backward_scratch_bytes", "conv3p_forward_f32", "conv3p_forward_ex_f32", "conv3p_selu_backward_f32", "conv3p_backward_f32",
+    "conv3p_plan_stats", "conv3p_plan_publish_stats", "conv3p_scratch_bytes", "conv3p_backward_scratch_bytes", "conv3p_forward_f32", "conv3p_forward_ex_f32", "conv3p_selu_backward_f32", "conv3p_backward_f32",
     "conv3p_op_workspace_bytes", "conv3p_op_backward_workspace_bytes", "conv3p_op_forward_f32", "conv3p_op_backward_f32",
     "conv3p_host_workspace_bytes", "conv3p_host_forward_f32", "conv3p_host_backward_f32",
     "conv3p_status_string", "conv3p_last_cuda_error", "conv3p_abi_version", "conv3p_launch_count",
@@ -68,6 +68,7 @@ def _declare(L):
     L.conv3p_plan_build_f32.argtypes = [gp, vp, vp, sz, vp]
     L.conv3p_plan_build_backward.argtypes = [gp, vp, vp, sz, vp]
     L.conv3p_plan_stats.argtypes = [gp, vp, C.POINTER(PlanStats), vp]
+    L.conv3p_plan_publish_stats.argtypes = [gp, vp, vp, vp]
     L.conv3p_scratch_bytes.argtypes = [gp, i, i]
     L.conv3p_scratch_bytes.restype = sz
     L.conv3p_backward_scratch_bytes.argtypes = [gp, i, i]

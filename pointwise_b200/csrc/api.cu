@@ -87,6 +87,13 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, int S, long
   out[w] = s;
 }
 
+// The plan's counters written straight into MAPPED pinned host memory by a one-warp kernel: no copy engine is
+// involved, so the deferred overflow check never queues behind (or in front of) an application's bulk copies.
+__global__ void k_publish_header(const long long* __restrict__ header, volatile long long* host_out) {
+  if (threadIdx.x < H_SLOTS) host_out[threadIdx.x] = header[threadIdx.x];
+  __threadfence_system();
+}
+
 int launch_reduce_partials(const float* partial, int S, long long nW, float* out, const long long* plan_header,
                            cudaStream_t stream) {
   {
@@ -353,6 +360,19 @@ int conv3p_plan_stats(const conv3p_geom_t* geom, const void* plan, conv3p_plan_s
   out->backward_pairs = h[H_BWD_PAIRS];
   out->overflow = (h[H_OVERFLOW] != 0 || h[H_CURSOR] > geom->pair_capacity) ? 1 : 0;
   out->has_backward = h[H_HAS_BWD] != 0;
+  return CONV3P_OK;
+}
+
+int conv3p_plan_publish_stats(const conv3p_geom_t* geom, const void* plan, long long* host_mapped16,
+                              conv3p_stream_t stream) {
+  if (!host_mapped16) return CONV3P_ERR_INVALID_ARGUMENT;
+  conv3p_plan_layout_t L;
+  int st = compute_layout(geom, &L);
+  if (st) return st;
+  if (!plan) return CONV3P_ERR_INVALID_ARGUMENT;
+  k_publish_header<<<1, 32, 0, stream>>>(reinterpret_cast<const long long*>(static_cast<const char*>(plan) + L.header),
+                                         host_mapped16);
+  C3P_LAUNCH_CHECK("k_publish_header");
   return CONV3P_OK;
 }
 

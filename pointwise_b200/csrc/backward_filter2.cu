@@ -56,12 +56,20 @@ struct W2Args {
 template <int GP>
 struct W2Map {
   static constexpr int CS = 4 / GP;   // cells stacked in one accumulator
-  // number of virtual accumulators
-  __host__ __device__ static int count(int Cout) { return GP == 4 ? C3P_NCELL * (Cout / 128) : (C3P_NCELL + CS - 1) / CS; }
+  // number of virtual accumulators; mbs = log2(128-channel blocks per cell) (GP == 4 only)
+  __host__ __device__ static int count(int mbs) { return GP == 4 ? C3P_NCELL << mbs : (C3P_NCELL + CS - 1) / CS; }
   // sub-mask (CS bits) of the accumulator's cells that have members in a tile with cell mask m
-  __host__ __device__ static unsigned cells(unsigned m, int va, int Cout) {
-    if (GP == 4) return (m >> (va / (Cout / 128))) & 1u;
+  __host__ __device__ static unsigned cells(unsigned m, int va, int mbs) {
+    if (GP == 4) return (m >> (va >> mbs)) & 1u;
     return (m >> (va * CS)) & ((1u << CS) - 1u);
+  }
+  // bit i: accumulator va0 + i (i < n) has members in a tile with cell mask m
+  __host__ __device__ static unsigned pass_mask(unsigned m, int va0, int n, int mbs) {
+    if (GP == 4 && mbs == 0) return (m >> va0) & ((n >= 32) ? ~0u : ((1u << n) - 1u));
+    unsigned r = 0;
+    for (int i = 0; i < n; ++i)
+      if (cells(m, va0 + i, mbs)) r |= 1u << i;
+    return r;
   }
 };
 
@@ -74,8 +82,8 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Cin = a.Cin, Cout = a.Cout, FG = a.FG, NGS = a.NGS, NXB = a.NXB;
   const int xp = Cin / 32;                             // panels of the input rows
-  const int MB = GP == 4 ? Cout / 128 : 1;             // 128-channel blocks per cell
-  const int NVA = W2Map<GP>::count(Cout);
+  const int mbs = (GP == 4 && Cout == 256) ? 1 : 0;    // log2(128-channel blocks per cell)
+  const int NVA = W2Map<GP>::count(mbs);
   const uint32_t x_half = (uint32_t)xp * PANEL;
   unsigned char* g_base = smem;                                     // NGS stages x (hi, lo)
   unsigned char* x_base = g_base + (size_t)NGS * 2 * g_half;        // NXB buffers x (hi, lo)
@@ -119,12 +127,7 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
   const uint32_t tmem = tmem_slot;
 
   // mask of the pass's accumulators that have members in a tile with cell mask m (bit = accumulator - va0)
-  auto pass_vas = [&](unsigned m, int va0, int va1) -> unsigned {
-    unsigned r = 0;
-    for (int va = va0; va < va1; ++va)
-      if (W2Map<GP>::cells(m, va, Cout)) r |= 1u << (va - va0);
-    return r;
-  };
+  auto pass_vas = [&](unsigned m, int va0, int va1) -> unsigned { return W2Map<GP>::pass_mask(m, va0, va1 - va0, mbs); };
 
   if (warp < NPW) {
     // =========================== producers ===========================================================
@@ -162,15 +165,16 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
       const long long tile = tile_lo + (s.h >> 12);
 #pragma unroll
       for (int cs = 0; cs < CS; ++cs) {
-        const int f = GP == 4 ? va / MB : va * CS + cs;
-        const int ch0 = GP == 4 ? (va % MB) * 128 : 0;
+        const int f = GP == 4 ? va >> mbs : va * CS + cs;
+        const int ch0 = GP == 4 ? (va & ((1 << mbs) - 1)) * 128 : 0;
         const float* src = a.g_store + (((size_t)tile * PTS + s.it[cs].p) * C3P_NCELL + f) * Cout + ch0 + l8 * 4;
 #pragma unroll
         for (int kc = 0; kc < GP; ++kc)
           v[cs * GP + kc] = s.it[cs].n > 0 ? ldg4(src + kc * PANEL_K) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    int visit = 0, g = 0;
+    int g_slot = 0, x_slot = 0;
+    uint32_t g_wrap = 0, x_wrap = 0;   // completed trips around the G ring / the X buffers
     // One stage of look-ahead: the next stage's items, with their first list ids (gather mode) or their G rows
     // (store mode) in flight.  (Three stages were measured slower: register moves of loaded values stall like
     // uses, and the extra registers spill.)
@@ -206,8 +210,9 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
         pass_mask |= mask;
         // ---- input rows of the tile -> X panels (hi/lo) ---------------------------------------------------
         {
-          const int xb = visit % NXB, use = visit / NXB;
-          if (use >= 1) mbar_wait(&x_empty[xb], (uint32_t)((use - 1) & 1));
+          const int xb = x_slot;
+          if (x_wrap >= 1) mbar_wait(&x_empty[xb], (x_wrap - 1) & 1u);
+          if (++x_slot == NXB) { x_slot = 0; ++x_wrap; }
           unsigned char* xs = x_base + (size_t)xb * 2 * x_half;
           const float* xr = a.input + (size_t)(row >= 0 ? row : 0) * Cin + l8 * 4;
           for (int pnl = 0; pnl < xp; ++pnl) {
@@ -226,7 +231,9 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[i] = ahead_rows[i];
           pull(ahead, ahead_rows);
-          const int slot = g % NGS, use = g / NGS;
+          const int slot = g_slot;
+          const uint32_t use = g_wrap;
+          if (++g_slot == NGS) { g_slot = 0; ++g_wrap; }
           unsigned char* stage = g_base + (size_t)slot * 2 * g_half;
           bool waited = false;
 #pragma unroll
@@ -234,14 +241,14 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
             if (!FROM_STORE) {
               int nmax = max(cur.it[cs].n, __shfl_xor_sync(C3P_FULL_MASK, cur.it[cs].n, 8));
               nmax = max(nmax, __shfl_xor_sync(C3P_FULL_MASK, nmax, 16));
-              const int ch0 = GP == 4 ? ((cur.h & 255) % MB) * 128 : 0;
+              const int ch0 = GP == 4 ? ((cur.h & 255) & ((1 << mbs) - 1)) * 128 : 0;
               float4 part[GP];
               g2_gather<GP, 8 / GP, true>(part, cur.it[cs], nmax, a.grad_out, Cout, ch0, a.rows, a.weights, l8, max_row);
 #pragma unroll
               for (int kc = 0; kc < GP; ++kc) acc[cs * GP + kc] = part[kc];
             }
             if (!waited) {
-              if (use >= 1) mbar_wait(&g_empty[slot], (uint32_t)((use - 1) & 1));
+              if (use >= 1) mbar_wait(&g_empty[slot], (use - 1) & 1u);
               waited = true;
             }
             unsigned char* dst = stage + panel_chunk_offset_mn(cur.it[cs].p, l8);
@@ -252,9 +259,7 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&g_full[slot]);
-          ++g;
         }
-        ++visit;
       }
       // ---- flush this pass's accumulators: partial[cta][f][k][c] = D[lane(c), k] ----------------------------
       mbar_wait(&acc_full, (uint32_t)(pass & 1));
@@ -264,8 +269,8 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
         const int L = sub * 32 + lane;                     // TMEM lane
         for (int ai = warp >> 2; ai < va1 - va0; ai += NPW / 4) {
           const int va = va0 + ai;
-          const int f = GP == 4 ? va / MB : va * CS + L / (GP * 32);
-          const int c = GP == 4 ? (va % MB) * 128 + L : L % (GP * 32);
+          const int f = GP == 4 ? va >> mbs : va * CS + L / (GP * 32);
+          const int c = GP == 4 ? (va & ((1 << mbs) - 1)) * 128 + L : L % (GP * 32);
           const bool live = (pass_mask >> ai) & 1u;
           float* dst = a.partial + ((size_t)blockIdx.x * C3P_NCELL + (f < C3P_NCELL ? f : 0)) * Cin * Cout;
           for (int k0 = 0; k0 < Cin; k0 += 32) {
@@ -291,7 +296,8 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
     // =========================== MMA issuer (one thread) ===============================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32_mn(128, Cin);
-      int visit = 0, gs = 0;
+      int g_slot = 0, x_slot = 0;
+      uint32_t g_phase = 0, x_phase = 0;
       for (int pass = 0; pass < npass; ++pass) {
         const int va0 = pass * FG, va1 = min(NVA, va0 + FG);
         unsigned started = 0;
@@ -302,14 +308,16 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
         for (long long tile = tile_lo; tile < tile_hi; ++tile) {
           const unsigned mask = pass_vas(__ldg(a.g_mask + tile), va0, va1);
           if (!mask) continue;
-          const int xb = visit % NXB;
-          mbar_wait(&x_full[xb], (uint32_t)((visit / NXB) & 1));
+          const int xb = x_slot;
+          mbar_wait(&x_full[xb], x_phase);
+          if (++x_slot == NXB) { x_slot = 0; x_phase ^= 1u; }
           const uint32_t x_hi = smem_u32(x_base + (size_t)xb * 2 * x_half), x_lo = x_hi + x_half;
           const int ai_last = 31 - __clz(mask);
           for (unsigned todo = mask; todo; todo &= todo - 1) {
             const int ai = __ffs(todo) - 1;
-            const int slot = gs % NGS;
-            mbar_wait(&g_full[slot], (uint32_t)((gs / NGS) & 1));
+            const int slot = g_slot;
+            mbar_wait(&g_full[slot], g_phase);
+            if (++g_slot == NGS) { g_slot = 0; g_phase ^= 1u; }
             tc_fence_after_sync();
             const uint32_t g_hi = smem_u32(g_base + (size_t)slot * 2 * g_half), g_lo = g_hi + g_half;
             const uint32_t d = tmem + (uint32_t)(ai * Cin);
@@ -325,9 +333,7 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
             started |= 1u << ai;
             mma_commit(&g_empty[slot]);
             if (ai == ai_last) mma_commit(&x_empty[xb]);
-            ++gs;
           }
-          ++visit;
         }
         mma_commit(&acc_full);
       }
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
           const unsigned cellmask = __ldg(a.g_mask + tile);
           for (unsigned todo = pass_vas(cellmask, va0, va1); todo; todo &= todo - 1) {
             const int va = va0 + __ffs(todo) - 1;
-            const unsigned sub = W2Map<GP>::cells(cellmask, va, Cout);
+            const unsigned sub = W2Map<GP>::cells(cellmask, va, mbs);
             const int slot = g & (W2_NIS - 1), use = g / W2_NIS;
             if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
             hdr[slot] = va | ((int)sub << 8) | ((int)(tile - tile_lo) << 12);
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
 #pragma unroll
             for (int cs = 0; cs < CS; ++cs) {
               if (!((sub >> cs) & 1u)) continue;
-              const int f = GP == 4 ? va / MB : va * CS + cs;
+              const int f = GP == 4 ? va >> mbs : va * CS + cs;
               bulk_copy_g2s(items + (slot * CS + cs) * PTS, a.g_items + (tile * C3P_NCELL + f) * PTS,
                             PTS * sizeof(uint2), &it_full[slot]);
             }

@@ -141,6 +141,36 @@ def _poll_pending_checks() -> None:
         raise err
 
 
+class _StatsSlots:
+    """Pool of 128-byte slots of pinned (device-addressable) host memory that plans publish their counters into."""
+    _free: list = []
+    _busy: list = []       # (slot, event): released by a plan that died before its counters were read
+    _blocks: list = []
+
+    @classmethod
+    def take(cls) -> torch.Tensor:
+        if cls._busy:
+            still = []
+            for slot, ev in cls._busy:
+                if ev.query():
+                    cls._free.append(slot)
+                else:
+                    still.append((slot, ev))
+            cls._busy = still
+        if not cls._free:
+            block = torch.zeros(64 * 16, dtype=torch.int64).pin_memory()
+            cls._blocks.append(block)
+            cls._free.extend(block[i * 16:(i + 1) * 16] for i in range(64))
+        return cls._free.pop()
+
+    @classmethod
+    def give(cls, slot: torch.Tensor, pending_event) -> None:
+        if pending_event is None:
+            cls._free.append(slot)
+        else:
+            cls._busy.append((slot, pending_event))     # the publishing kernel may still be in flight
+
+
 class NeighborPlan:
     """Voxel-sorted neighbour structure of one batch of clouds for one (stride, voxel_size).
 
@@ -179,7 +209,7 @@ class NeighborPlan:
         self.has_backward = False
         self._stats = None
         self._stats_event = None
-        self._stats_host = None
+        self._stats_slot = None
         L = _lib.lib()
         self._key = key = (self.B, self.N, self.stride, self.voxel_size)
         pts = self.B * self.N
@@ -228,12 +258,21 @@ class NeighborPlan:
     # ---- deferred overflow check -----------------------------------------------------------------
     def _enqueue_header_copy(self) -> None:
         import weakref
-        self._stats_host = torch.empty(16, dtype=torch.int64).pin_memory()
-        hdr = self.buffer[self.layout.header:self.layout.header + 128].view(torch.int64)
-        self._stats_host.copy_(hdr, non_blocking=True)
+        self._stats_slot = _StatsSlots.take()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().conv3p_plan_publish_stats(self.geom, _ptr(self.buffer),
+                                                            C.c_void_p(self._stats_slot.data_ptr()),
+                                                            _stream_ptr(self.device)))
         self._stats_event = torch.cuda.Event()
         self._stats_event.record(torch.cuda.current_stream(self.device))
         _pending_checks.append(weakref.ref(self))
+
+    def __del__(self):
+        slot = getattr(self, "_stats_slot", None)
+        if slot is not None:
+            ev = getattr(self, "_stats_event", None)
+            _StatsSlots.give(slot, ev)
+            self._stats_slot = None
 
     def verify(self, block: bool = True) -> bool:
         """Looks at the deferred copy of the plan's counters.  Returns False when it has not arrived yet and
@@ -246,7 +285,9 @@ class NeighborPlan:
         elif not ev.query():
             return False
         self._stats_event = None
-        h = self._stats_host.tolist()
+        h = self._stats_slot.tolist()
+        _StatsSlots.give(self._stats_slot, None)
+        self._stats_slot = None
         st = _lib.PlanStats()
         st.total_pairs, st.backward_pairs = int(h[0]), int(h[2])
         st.overflow = 1 if (h[1] != 0 or h[0] > self.capacity) else 0
