@@ -217,7 +217,8 @@ long long conv3p_launch_count(int reset);
  * the fp32 engines), 1 = fp32 SIMT only (warp-per-point or tile kernels by channel count), 2 = tensor cores (3xTF32)
  * where supported, 3 = generic fp32 tile kernels only (no tensor cores, no warp-per-point kernels).  Higher bits are
  * ablation flags for A/B timing (tools/engine_timing.py, tools/ab_backward.py): 32 = phase timers of the gather+MMA
- * kernel, 256 = no G store shared between the two gradient kernels, 1024 = first version of the small-channel
+ * kernel, 256 = no G store shared between the two gradient kernels, 512 = three TF32 products (3xTF32) instead of
+ * one TF32 product + BF16 correction products in the tensor-core kernels, 1024 = first version of the small-channel
  * kernels.  Returns the previous value.  Process-wide (a test/benchmark knob, not part of the operator's state). */
 int conv3p_set_engine(int engine);
 

@@ -73,21 +73,30 @@ struct W2Map {
   }
 };
 
-template <bool FROM_STORE, int GP, int PTS>
+// Bytes of one input (X) buffer: the TF32 hi panels + the second part (fp32 lo panels, or the BF16 correction panels
+// [hi ; lo] stacked along the point index: ceil(Cin / 64) panels of 2 * PTS rows) -- sized for either split.
+__host__ __device__ inline uint32_t w2_x_half(int Cin, int pts) { return (uint32_t)(Cin / 32) * pts * PANEL_ROW_BYTES; }
+__host__ __device__ inline uint32_t w2_x_second(int Cin, int pts) { return (uint32_t)((Cin + 63) / 64) * 2u * pts * PANEL_ROW_BYTES; }
+
+// BF16C: TF32 main product + BF16 correction products (tc_common.cuh); false = three TF32 products (engine flag 512).
+template <bool FROM_STORE, int GP, int PTS, bool BF16C>
 __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(const W2Args a) {
   constexpr int NPW = PTS / 4;                         // producer warps: one quarter-warp per row of the tile
   constexpr int CS = W2Map<GP>::CS;
   constexpr uint32_t PANEL = (uint32_t)PTS * PANEL_ROW_BYTES;   // PTS rows x 32 fp32
-  constexpr uint32_t g_half = 4u * PANEL;              // hi (or lo) part of a G stage: 4 panels = 128 lanes
+  constexpr uint32_t PANEL16 = 2u * PANEL;             // BF16 correction panel: 2 * PTS rows x 64 bf16 ([lo ; hi] or [hi ; lo])
+  constexpr uint32_t g_half = 4u * PANEL;              // hi part of a G stage: 4 panels = 128 lanes; the second part
+                                                       // (fp32 lo panels, or 2 BF16 correction panels) has the same size
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Cin = a.Cin, Cout = a.Cout, FG = a.FG, NGS = a.NGS, NXB = a.NXB;
   const int xp = Cin / 32;                             // panels of the input rows
   const int mbs = (GP == 4 && Cout == 256) ? 1 : 0;    // log2(128-channel blocks per cell)
   const int NVA = W2Map<GP>::count(mbs);
-  const uint32_t x_half = (uint32_t)xp * PANEL;
-  unsigned char* g_base = smem;                                     // NGS stages x (hi, lo)
-  unsigned char* x_base = g_base + (size_t)NGS * 2 * g_half;        // NXB buffers x (hi, lo)
-  uint2* items = reinterpret_cast<uint2*>(x_base + (size_t)NXB * 2 * x_half);  // [NIS][CS][PTS]
+  const uint32_t x_half = w2_x_half(Cin, PTS);
+  const uint32_t x_buf = x_half + w2_x_second(Cin, PTS);
+  unsigned char* g_base = smem;                                     // NGS stages x (hi, second)
+  unsigned char* x_base = g_base + (size_t)NGS * 2 * g_half;        // NXB buffers x (hi, second)
+  uint2* items = reinterpret_cast<uint2*>(x_base + (size_t)NXB * x_buf);  // [NIS][CS][PTS]
   __shared__ uint64_t g_full[W2_MAX_NGS], g_empty[W2_MAX_NGS], x_full[2], x_empty[2], it_full[W2_NIS],
       it_empty[W2_NIS], acc_full, acc_empty;
   __shared__ uint32_t tmem_slot;
@@ -213,12 +222,19 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
           const int xb = x_slot;
           if (x_wrap >= 1) mbar_wait(&x_empty[xb], (x_wrap - 1) & 1u);
           if (++x_slot == NXB) { x_slot = 0; ++x_wrap; }
-          unsigned char* xs = x_base + (size_t)xb * 2 * x_half;
+          unsigned char* xs = x_base + (size_t)xb * x_buf;
           const float* xr = a.input + (size_t)(row >= 0 ? row : 0) * Cin + l8 * 4;
           for (int pnl = 0; pnl < xp; ++pnl) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row >= 0) v = ldg4(xr + pnl * PANEL_K);
-            g2_store_split(xs + (size_t)pnl * PANEL + panel_chunk_offset_mn(q, l8), x_half, v);
+            unsigned char* hi_dst = xs + (size_t)pnl * PANEL + panel_chunk_offset_mn(q, l8);
+            if (BF16C) {   // B side of the correction product: rows [0, PTS) hi, [PTS, 2 PTS) lo
+              unsigned char* c = xs + x_half + (size_t)(pnl >> 1) * PANEL16;
+              const int j = (pnl & 1) * 32 + 4 * l8;
+              g2_store_split16(hi_dst, c + panel_offset16(PTS + q, j), c + panel_offset16(q, j), v);
+            } else {
+              g2_store_split(hi_dst, x_half, v);
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -251,10 +267,19 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
               if (use >= 1) mbar_wait(&g_empty[slot], (use - 1) & 1u);
               waited = true;
             }
-            unsigned char* dst = stage + panel_chunk_offset_mn(cur.it[cs].p, l8);
+            const int p = cur.it[cs].p;
+            unsigned char* dst = stage + panel_chunk_offset_mn(p, l8);
 #pragma unroll
-            for (int kc = 0; kc < GP; ++kc)
-              g2_store_split(dst + (size_t)(cs * GP + kc) * PANEL, g_half, acc[cs * GP + kc]);
+            for (int kc = 0; kc < GP; ++kc) {
+              const int pi = cs * GP + kc;                  // 32-lane panel of the accumulator's M = 128
+              if (BF16C) {   // A side of the correction product: rows [0, PTS) lo, [PTS, 2 PTS) hi
+                unsigned char* c = stage + g_half + (size_t)(pi >> 1) * PANEL16;
+                const int j = (pi & 1) * 32 + 4 * l8;
+                g2_store_split16(dst + (size_t)pi * PANEL, c + panel_offset16(p, j), c + panel_offset16(PTS + p, j), acc[pi]);
+              } else {
+                g2_store_split(dst + (size_t)pi * PANEL, g_half, acc[pi]);
+              }
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -295,7 +320,7 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
   } else if (warp == NPW) {
     // =========================== MMA issuer (one thread) ===============================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_mn(128, Cin);
+      const uint32_t idesc = make_idesc_tf32_mn(128, Cin), idesc16 = make_idesc_bf16_mn(128, Cin);
       int g_slot = 0, x_slot = 0;
       uint32_t g_phase = 0, x_phase = 0;
       for (int pass = 0; pass < npass; ++pass) {
@@ -311,7 +336,7 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
           const int xb = x_slot;
           mbar_wait(&x_full[xb], x_phase);
           if (++x_slot == NXB) { x_slot = 0; x_phase ^= 1u; }
-          const uint32_t x_hi = smem_u32(x_base + (size_t)xb * 2 * x_half), x_lo = x_hi + x_half;
+          const uint32_t x_hi = smem_u32(x_base + (size_t)xb * x_buf), x_lo = x_hi + x_half;
           const int ai_last = 31 - __clz(mask);
           for (unsigned todo = mask; todo; todo &= todo - 1) {
             const int ai = __ffs(todo) - 1;
@@ -327,8 +352,17 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
               const uint64_t dgh = make_smem_desc_mn(g_hi + adv, PANEL), dgl = make_smem_desc_mn(g_lo + adv, PANEL);
               const uint64_t dxh = make_smem_desc_mn(x_hi + adv, PANEL), dxl = make_smem_desc_mn(x_lo + adv, PANEL);
               mma_tf32(d, dgh, dxh, idesc, (((started >> ai) & 1u) | (unsigned)j) ? 1u : 0u);
-              mma_tf32(d, dgl, dxh, idesc, 1u);
-              mma_tf32(d, dgh, dxl, idesc, 1u);
+              if (!BF16C) {
+                mma_tf32(d, dgl, dxh, idesc, 1u);
+                mma_tf32(d, dgh, dxl, idesc, 1u);
+              }
+            }
+            if (BF16C) {   // [G_lo ; G_hi]^T x [X_hi ; X_lo]: 2 * PTS rows in steps of 16
+#pragma unroll
+              for (int j = 0; j < PTS / 8; ++j) {
+                const uint32_t adv = (uint32_t)j * 2048u;
+                mma_bf16(d, make_smem_desc_mn16(g_lo + adv, PANEL16), make_smem_desc_mn16(x_lo + adv, PANEL16), idesc16, 1u);
+              }
             }
             started |= 1u << ai;
             mma_commit(&g_empty[slot]);
@@ -405,7 +439,7 @@ static bool w2_config(int N, long long capacity, int Cin, int Cout, W2Config* c)
     const int pts = order[o][0], nxb = order[o][1];
     if (forced.first && pts != forced.first) continue;
     const size_t panel = (size_t)pts * PANEL_ROW_BYTES;
-    const size_t g_stage = 2 * 4 * panel, x_buf = 2 * (size_t)(Cin / 32) * panel;
+    const size_t g_stage = 2 * 4 * panel, x_buf = (size_t)w2_x_half(Cin, pts) + w2_x_second(Cin, pts);
     const size_t items = (size_t)W2_NIS * CS * pts * sizeof(uint2);
     if (items + nxb * x_buf + 2 * g_stage > budget) continue;
     int ngs = (int)((budget - items - nxb * x_buf) / g_stage);
@@ -438,9 +472,9 @@ size_t backward_filter2_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout)
   return group_items_bytes(pts, c.PTS) + align_up(sizeof(float) * (size_t)ctas * C3P_NCELL * Cin * Cout);
 }
 
-template <bool FROM_STORE, int GP, int PTS>
+template <bool FROM_STORE, int GP, int PTS, bool BF16C>
 static int w2_launch(const W2Args& a, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = k_backward_filter2<FROM_STORE, GP, PTS>;
+  auto kern = k_backward_filter2<FROM_STORE, GP, PTS, BF16C>;
   const int st = ensure_dynamic_smem(kern, 227 * 1024 - 1024);
   if (st) return st;
   {
@@ -451,16 +485,16 @@ static int w2_launch(const W2Args& a, int grid, size_t smem, cudaStream_t stream
   return CONV3P_OK;
 }
 
-template <bool FROM_STORE>
+template <bool FROM_STORE, bool BF16C>
 static int w2_dispatch(const W2Config& c, const W2Args& a, int grid, cudaStream_t stream) {
   if (c.PTS == 64) {
-    if (c.GP == 4) return w2_launch<FROM_STORE, 4, 64>(a, grid, c.smem, stream);
-    if (c.GP == 2) return w2_launch<FROM_STORE, 2, 64>(a, grid, c.smem, stream);
-    return w2_launch<FROM_STORE, 1, 64>(a, grid, c.smem, stream);
+    if (c.GP == 4) return w2_launch<FROM_STORE, 4, 64, BF16C>(a, grid, c.smem, stream);
+    if (c.GP == 2) return w2_launch<FROM_STORE, 2, 64, BF16C>(a, grid, c.smem, stream);
+    return w2_launch<FROM_STORE, 1, 64, BF16C>(a, grid, c.smem, stream);
   }
-  if (c.GP == 4) return w2_launch<FROM_STORE, 4, 32>(a, grid, c.smem, stream);
-  if (c.GP == 2) return w2_launch<FROM_STORE, 2, 32>(a, grid, c.smem, stream);
-  return w2_launch<FROM_STORE, 1, 32>(a, grid, c.smem, stream);
+  if (c.GP == 4) return w2_launch<FROM_STORE, 4, 32, BF16C>(a, grid, c.smem, stream);
+  if (c.GP == 2) return w2_launch<FROM_STORE, 2, 32, BF16C>(a, grid, c.smem, stream);
+  return w2_launch<FROM_STORE, 1, 32, BF16C>(a, grid, c.smem, stream);
 }
 
 int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const float* grad_out, const float* input,
@@ -486,7 +520,10 @@ int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const flo
   a.g_items = gi.items; a.g_rowid = gi.rowid; a.g_mask = gi.mask; a.partial = partial; a.g_store = g_store;
   a.total_points = pts; a.tiles = gi.subtiles; a.Cin = Cin; a.Cout = Cout;
   a.FG = c.FG; a.NGS = c.NGS; a.NXB = c.NXB;
-  st = g_store ? w2_dispatch<true>(c, a, grid, stream) : w2_dispatch<false>(c, a, grid, stream);
+  if (engine_flag(512))   // three TF32 products (A/B timing, accuracy reference)
+    st = g_store ? w2_dispatch<true, false>(c, a, grid, stream) : w2_dispatch<false, false>(c, a, grid, stream);
+  else
+    st = g_store ? w2_dispatch<true, true>(c, a, grid, stream) : w2_dispatch<false, true>(c, a, grid, stream);
   if (st) return st;
   return launch_reduce_partials(partial, grid, nW, grad_filter, v.header, stream);
 }

@@ -206,7 +206,9 @@ __device__ __noinline__ void g2_epilogue(float* out, long long out_stride, int a
   }
 }
 
-template <int NKC, bool WEIGHTED, bool TIMED>
+// BF16C: the two correction products of the hi/lo split run as one BF16 MMA chain (tc_common.cuh); false = three TF32
+// products (3xTF32, engine flag 512: A/B timing and the accuracy reference of the tests).
+template <int NKC, bool WEIGHTED, bool TIMED, bool BF16C>
 __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int Nout = a.Nout, NAS = a.NAS, NWU = a.NWU;
@@ -376,11 +378,22 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
           }
         }
         G2_PHASE(6);
-        {
-          const uint32_t o = panel_chunk_offset(c0.p, l8);
+        // operand stage = [hi panel (fp32, TF32 values) | second panel]; second panel = lo (fp32) for 3xTF32, or the
+        // BF16 correction panel [lo (32 ch) | hi (32 ch)] per row
+        auto store_row = [&](int p, const float4 (&v)[NKC]) {
+          const uint32_t o = panel_chunk_offset(p, l8);
+          if (BF16C) {
+            const uint32_t oc = 128 * PANEL_ROW_BYTES + (uint32_t)p * PANEL_ROW_BYTES + ((uint32_t)(l8 & 1) << 3);
+            const uint32_t c_lo = oc + ((((uint32_t)l8 >> 1) ^ ((uint32_t)p & 7u)) << 4);
+            const uint32_t c_hi = oc + (((4u + ((uint32_t)l8 >> 1)) ^ ((uint32_t)p & 7u)) << 4);
 #pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, 128 * PANEL_ROW_BYTES, acc[kc]);
-        }
+            for (int kc = 0; kc < NKC; ++kc) g2_store_split16(stage[kc] + o, stage[kc] + c_lo, stage[kc] + c_hi, v[kc]);
+          } else {
+#pragma unroll
+            for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, 128 * PANEL_ROW_BYTES, v[kc]);
+          }
+        };
+        store_row(c0.p, acc);
         const int nmax1 = warp_max(c1.n);
         if (nmax1 > 0) {
           g2_gather<NKC, 4, WEIGHTED>(acc, c1, nmax1, a.src, (int)a.src_stride, col, a.rows, a.weights, l8, max_row);
@@ -390,18 +403,15 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
               *reinterpret_cast<float4*>(gs + (size_t)c1.p * C3P_NCELL * a.Csrc + kc * PANEL_K) = acc[kc];
           }
         }
-        {
+        if (nmax1 > 0) {
+          store_row(c1.p, acc);
+        } else {   // all-empty second repetition: zero the row's chunk in both panels (any layout: 2 x 16 bytes)
           const uint32_t o = panel_chunk_offset(c1.p, l8);
-          if (nmax1 > 0) {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int kc = 0; kc < NKC; ++kc) g2_store_split(stage[kc] + o, 128 * PANEL_ROW_BYTES, acc[kc]);
-          } else {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int kc = 0; kc < NKC; ++kc) {
-              sts128(stage[kc] + o, z);
-              sts128(stage[kc] + o + 128 * PANEL_ROW_BYTES, z);
-            }
+          for (int kc = 0; kc < NKC; ++kc) {
+            sts128(stage[kc] + o, z);
+            sts128(stage[kc] + o + 128 * PANEL_ROW_BYTES, z);
           }
         }
         fence_proxy_async();
@@ -439,7 +449,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
       // Per 32-channel panel: 4 K steps of (A_hi W_hi, A_lo W_hi), then 4 K steps of A_hi W_lo, so the lo half of
       // a weight panel is needed 512 MMA cycles after its hi half and the hi unit is released before the lo unit.
       if (lane == 0) {
-        const uint32_t idesc = make_idesc_tf32(128, Nout);
+        const uint32_t idesc = make_idesc_tf32(128, Nout), idesc16 = make_idesc_bf16(128, Nout);
         const uint64_t a_desc0 = make_smem_desc(s_a), w_desc0 = make_smem_desc(s_w);
         const uint64_t a_lo_off = (uint64_t)((128 * PANEL_ROW_BYTES) >> 4);
         const uint64_t a_step = (uint64_t)(G2_A_STAGE >> 4), w_step = (uint64_t)(unit_bytes >> 4);
@@ -473,7 +483,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
                 for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
                   const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
                   mma_tf32(d, dah + adv, dwh + adv, idesc, acc_flag);
-                  mma_tf32(d, dal + adv, dwh + adv, idesc, 1u);
+                  if (!BF16C) mma_tf32(d, dal + adv, dwh + adv, idesc, 1u);
                   acc_flag = 1u;
                 }
                 if (t == t_last) mma_commit(bar(G2B_W_EMPTY, us[2 * kc]));
@@ -484,7 +494,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
 #pragma unroll
                 for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
                   const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
-                  mma_tf32(d, dah + adv, dwl + adv, idesc, 1u);
+                  // BF16C: [A_lo | A_hi] x [W_hi | W_lo], 64 bf16 of K in 4 steps of 16 (32 bytes each, like TF32's 8 x 4)
+                  if (BF16C) mma_bf16(d, dal + adv, dwl + adv, idesc16, 1u);
+                  else mma_tf32(d, dah + adv, dwl + adv, idesc, 1u);
                 }
                 mma_commit(bar(G2B_A_EMPTY, m_aslot));
                 if (t == t_last) mma_commit(bar(G2B_W_EMPTY, us[2 * kc + 1]));
@@ -701,12 +713,17 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
     C3P_LAUNCH_CHECK(name);
     return CONV3P_OK;
   };
-  if (a.debug & 32) {   // phase timers compiled in (tools/engine_timing.py)
-    if (c.NKC == 1) return weighted ? launch(k_gather_mma2<1, true, true>) : launch(k_gather_mma2<1, false, true>);
-    return weighted ? launch(k_gather_mma2<2, true, true>) : launch(k_gather_mma2<2, false, true>);
+  const bool tf32x3 = engine_flag(512);   // three TF32 products instead of TF32 + BF16 corrections (A/B, accuracy reference)
+  if (a.debug & 32) {   // phase timers compiled in (tools/engine_timing.py); production split only
+    if (c.NKC == 1) return weighted ? launch(k_gather_mma2<1, true, true, true>) : launch(k_gather_mma2<1, false, true, true>);
+    return weighted ? launch(k_gather_mma2<2, true, true, true>) : launch(k_gather_mma2<2, false, true, true>);
   }
-  if (c.NKC == 1) return weighted ? launch(k_gather_mma2<1, true, false>) : launch(k_gather_mma2<1, false, false>);
-  return weighted ? launch(k_gather_mma2<2, true, false>) : launch(k_gather_mma2<2, false, false>);
+  if (tf32x3) {
+    if (c.NKC == 1) return weighted ? launch(k_gather_mma2<1, true, false, false>) : launch(k_gather_mma2<1, false, false, false>);
+    return weighted ? launch(k_gather_mma2<2, true, false, false>) : launch(k_gather_mma2<2, false, false, false>);
+  }
+  if (c.NKC == 1) return weighted ? launch(k_gather_mma2<1, true, false, true>) : launch(k_gather_mma2<1, false, false, true>);
+  return weighted ? launch(k_gather_mma2<2, true, false, true>) : launch(k_gather_mma2<2, false, false, true>);
 }
 
 }  // namespace c3p

@@ -72,6 +72,48 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- BF16 correction products ------------------------------------------------------------------------------
+// The two correction terms of the split product, A_lo*B_hi + A_hi*B_lo, are ~2^-11 of the main term: they only need
+// ~8 significant bits, so they run as ONE kind::f16 MMA chain on BF16 operands with the two terms concatenated
+// along K -- A_c = [A_lo | A_hi], B_c = [B_hi | B_lo] -- at twice the K per instruction of kind::tf32 (16 against 8):
+// a third fewer tensor-core cycles and a third fewer shared-memory operand reads than three TF32 products, at
+// |error| <= ~2^-18 per product (hi = fp32 ROUNDED to an 11-bit significand, so |lo| <= 2^-11 |x|; BF16 rounding of
+// either factor of a correction term is 2^-9 relative).
+// A BF16 panel row is 128 B = 64 elements, 128B-swizzled like the fp32 panels (16-byte chunk c at c ^ (row & 7)).
+__host__ __device__ __forceinline__ uint32_t panel_offset16(int row, int j) {   // byte offset of bf16 element j (0..63)
+  return (uint32_t)row * PANEL_ROW_BYTES + ((((uint32_t)j >> 3) ^ ((uint32_t)row & 7u)) << 4) + (((uint32_t)j & 7u) << 1);
+}
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {      // D fp32 += A bf16 * B bf16, K-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16_mn(int M, int N) {   // both operands MN-major
+  return make_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+}
+// MN-major 16-bit operands: standard 128B swizzle, 8-row atoms of 1024 B along K (stride byte offset), 64-element
+// MN blocks `mn_block_stride` bytes apart (leading byte offset); one kind::f16 MMA consumes 16 rows.
+__device__ __forceinline__ uint64_t make_smem_desc_mn16(uint32_t smem_addr, uint32_t mn_block_stride) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((mn_block_stride >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                                   // layout type SWIZZLE_128B
+  return d;
+}
+// fp32 rounded to nearest into a 10-bit mantissa (the value kind::tf32 sees exactly); x - tf32_rn(x) is exact in fp32.
+__device__ __forceinline__ float tf32_rn(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+// {bf16(lo_elem) in bits [0,16), bf16(hi_elem) in bits [16,32)}: lo_elem is the one at the lower address
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -197,6 +239,17 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");

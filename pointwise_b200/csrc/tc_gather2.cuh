@@ -83,6 +83,26 @@ __device__ __forceinline__ void g2_store_split(uint32_t dst, uint32_t lo_offset,
   sts128(dst + lo_offset, make_float4(l0.x, l0.y, l1.x, l1.y));
 }
 
+// TF32 main panel + BF16 correction panel (tc_common.cuh, "BF16 correction products"): writes hi = tf32_rn(v) as fp32
+// at `hi_dst` and the BF16 pairs of lo = v - hi and of hi (8 bytes each) at `lo16_dst` / `hi16_dst`.
+__device__ __forceinline__ void g2_store_split16(uint32_t hi_dst, uint32_t lo16_dst, uint32_t hi16_dst, const float4& v) {
+  const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+  const float2 l0 = __fadd2_rn(make_float2(v.x, v.y), make_float2(-h.x, -h.y));
+  const float2 l1 = __fadd2_rn(make_float2(v.z, v.w), make_float2(-h.z, -h.w));
+  sts128(hi_dst, h);
+  sts64(lo16_dst, pack_bf16x2(l0.x, l0.y), pack_bf16x2(l1.x, l1.y));
+  sts64(hi16_dst, pack_bf16x2(h.x, h.y), pack_bf16x2(h.z, h.w));
+}
+__device__ __forceinline__ void g2_store_split16(unsigned char* hi_dst, unsigned char* lo16_dst, unsigned char* hi16_dst,
+                                                 const float4& v) {
+  const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+  const float2 l0 = __fadd2_rn(make_float2(v.x, v.y), make_float2(-h.x, -h.y));
+  const float2 l1 = __fadd2_rn(make_float2(v.z, v.w), make_float2(-h.z, -h.w));
+  *reinterpret_cast<float4*>(hi_dst) = h;
+  *reinterpret_cast<uint2*>(lo16_dst) = make_uint2(pack_bf16x2(l0.x, l0.y), pack_bf16x2(l1.x, l1.y));
+  *reinterpret_cast<uint2*>(hi16_dst) = make_uint2(pack_bf16x2(h.x, h.y), pack_bf16x2(h.z, h.w));
+}
+
 // 1 / x for x >= 1 (member counts): one MUFU.RCP, within 1 ulp.
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;

@@ -8,6 +8,8 @@
 // lists and the orientation of the weight panels differ.  The weights are pre-split (TF32 hi / lo), pre-transposed
 // and pre-swizzled ONCE per call into panel images, so one thread of the main kernel streams them with bulk async
 // copies (UBLKCP) signalled on mbarriers.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -16,8 +18,10 @@ namespace c3p {
 using namespace tc;
 
 // weights [27][Cin][Cout] -> panel images: for (f, kc, hl) a [R rows x 32 k] K-major 128B-swizzled panel
+// Second panel of a pair: the lo parts as fp32 (3xTF32, bf16c == 0) or the BF16 correction panel [W_hi | W_lo]
+// (64 bf16 per row) that multiplies the A-side panel [A_lo | A_hi] (tc_common.cuh).
 __global__ void k_prep_weight_panels(const float* __restrict__ filter, unsigned char* __restrict__ wp,
-                                     int Cin, int Cout, int transposed_out) {
+                                     int Cin, int Cout, int transposed_out, int bf16c) {
   // transposed_out == 0: rows = Cout (n = c), K = Cin (forward B operand, W^T)
   // transposed_out == 1: rows = Cin  (n = k), K = Cout (input-gradient B operand, W)
   const int R = transposed_out ? Cin : Cout;   // panel rows
@@ -33,10 +37,16 @@ __global__ void k_prep_weight_panels(const float* __restrict__ filter, unsigned 
     const int kk = kc * PANEL_K + k;
     const float w = transposed_out ? filter[((size_t)f * Cin + r) * Cout + kk]
                                    : filter[((size_t)f * Cin + kk) * Cout + r];
-    const float h = tf32_hi(w);
+    const float h = bf16c ? tf32_rn(w) : tf32_hi(w);
     unsigned char* base = wp + ((size_t)(f * nkc + kc) * 2) * R * PANEL_ROW_BYTES;
     *reinterpret_cast<float*>(base + panel_offset(r, k)) = h;
-    *reinterpret_cast<float*>(base + (size_t)R * PANEL_ROW_BYTES + panel_offset(r, k)) = w - h;
+    unsigned char* second = base + (size_t)R * PANEL_ROW_BYTES;
+    if (bf16c) {
+      *reinterpret_cast<__nv_bfloat16*>(second + panel_offset16(r, k)) = __float2bfloat16_rn(h);
+      *reinterpret_cast<__nv_bfloat16*>(second + panel_offset16(r, 32 + k)) = __float2bfloat16_rn(w - h);
+    } else {
+      *reinterpret_cast<float*>(second + panel_offset(r, k)) = w - h;
+    }
   }
 }
 
@@ -66,7 +76,7 @@ int launch_prep_weight_panels(const float* filter, void* wp, int Cin, int Cout, 
   {
     LaunchTimer timer_("k_prep_weight_panels", stream);
     k_prep_weight_panels<<<blocks, threads, 0, stream>>>(filter, static_cast<unsigned char*>(wp), Cin, Cout,
-                                                         transposed_out);
+                                                         transposed_out, engine_flag(512) ? 0 : 1);
   }
   C3P_LAUNCH_CHECK("k_prep_weight_panels");
   return CONV3P_OK;

@@ -33,6 +33,7 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
   const uint32_t tmem = tmem_slot;
   const bool probe_b32 = (split & 2) != 0;   // hardware probe: K-major operands stored with the 32B-base swizzle
   const bool probe_m64 = (split & 4) != 0;   // hardware probe: M = 64 (rows 64..127 of A are ignored)
+  const bool bf16c = (split & 8) != 0;       // the production split: TF32 main product + BF16 correction products
   const uint32_t idesc = make_idesc_tf32(probe_m64 ? 64 : 128, N);
   split &= 1;
 
@@ -43,21 +44,33 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
       const int r = e >> 3, c = e & 7;
       const float4 v = *reinterpret_cast<const float4*>(A + (size_t)r * K + kp * PANEL_K + c * 4);
       float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      if (bf16c) h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
       float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       if (!split) h = v;
       const uint32_t o = probe_b32 ? panel_chunk_offset_mn(r, c) : panel_chunk_offset(r, c);
       *reinterpret_cast<float4*>(a_hi + o) = h;
-      *reinterpret_cast<float4*>(a_lo + o) = l;
+      if (bf16c) {   // A_c = [A_lo | A_hi] as bf16
+        *reinterpret_cast<uint2*>(a_lo + panel_offset16(r, 4 * c)) = make_uint2(pack_bf16x2(l.x, l.y), pack_bf16x2(l.z, l.w));
+        *reinterpret_cast<uint2*>(a_lo + panel_offset16(r, 32 + 4 * c)) = make_uint2(pack_bf16x2(h.x, h.y), pack_bf16x2(h.z, h.w));
+      } else {
+        *reinterpret_cast<float4*>(a_lo + o) = l;
+      }
     }
     for (int e = tid; e < N * 8; e += 128) {
       const int r = e >> 3, c = e & 7;
       const float4 v = *reinterpret_cast<const float4*>(B + (size_t)r * K + kp * PANEL_K + c * 4);
       float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      if (bf16c) h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
       float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       if (!split) h = v;
       const uint32_t o = probe_b32 ? panel_chunk_offset_mn(r, c) : panel_chunk_offset(r, c);
       *reinterpret_cast<float4*>(b_hi + o) = h;
-      *reinterpret_cast<float4*>(b_lo + o) = l;
+      if (bf16c) {   // B_c = [B_hi | B_lo] as bf16
+        *reinterpret_cast<uint2*>(b_lo + panel_offset16(r, 4 * c)) = make_uint2(pack_bf16x2(h.x, h.y), pack_bf16x2(h.z, h.w));
+        *reinterpret_cast<uint2*>(b_lo + panel_offset16(r, 32 + 4 * c)) = make_uint2(pack_bf16x2(l.x, l.y), pack_bf16x2(l.z, l.w));
+      } else {
+        *reinterpret_cast<float4*>(b_lo + o) = l;
+      }
     }
     fence_proxy_async();
     __syncthreads();
@@ -71,10 +84,15 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
       for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
         const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
         mma_tf32(tmem, dah + adv, dbh + adv, idesc, (kp | ks) ? 1u : 0u);
-        if (split) {
+        if (split && !bf16c) {
           mma_tf32(tmem, dal + adv, dbh + adv, idesc, 1u);
           mma_tf32(tmem, dah + adv, dbl + adv, idesc, 1u);
         }
+      }
+      if (bf16c) {   // 64 bf16 of K in 4 steps of 16 (32 bytes)
+        const uint32_t idesc16 = make_idesc_bf16(128, N);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_bf16(tmem, dal + (uint64_t)(ks * 2), dbl + (uint64_t)(ks * 2), idesc16, 1u);
       }
       mma_commit(&done_bar);
     }
@@ -103,10 +121,13 @@ k_tc_selftest_mn(const float* __restrict__ A, const float* __restrict__ B, float
                  int split) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t panel = (uint32_t)K * PANEL_ROW_BYTES;   // one panel: K rows x 32 fp32
+  const bool bf16c = (split & 8) != 0;                    // TF32 main product + BF16 correction products
+  split &= 1;
   unsigned char* a_hi = smem;                             // 4 panels (M = 128)
-  unsigned char* a_lo = a_hi + 4 * panel;
+  unsigned char* a_lo = a_hi + 4 * panel;                 // (bf16c: 2 panels of 2K rows x 64 bf16: rows [0,K) lo, [K,2K) hi)
   unsigned char* b_hi = a_lo + 4 * panel;                 // N/32 panels
-  unsigned char* b_lo = b_hi + (N / 32) * panel;
+  unsigned char* b_lo = b_hi + (N / 32) * panel;          // (bf16c: ceil(N/64) panels of 2K rows: rows [0,K) hi, [K,2K) lo)
+  const uint32_t panel16 = 2u * panel;
   __shared__ uint64_t done_bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -123,21 +144,35 @@ k_tc_selftest_mn(const float* __restrict__ A, const float* __restrict__ B, float
     const int r = e >> 5, c = e & 31;
     const float4 v = *reinterpret_cast<const float4*>(A + (size_t)r * 128 + c * 4);
     float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    if (bf16c) h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
     const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
     if (!split) h = v;
     const uint32_t o = (uint32_t)(c >> 3) * panel + panel_chunk_offset_mn(r, c & 7);
     *reinterpret_cast<float4*>(a_hi + o) = h;
-    *reinterpret_cast<float4*>(a_lo + o) = l;
+    if (bf16c) {   // channel 4c: MN block (4c) >> 6, element (4c) & 63
+      unsigned char* pc = a_lo + (uint32_t)((4 * c) >> 6) * panel16;
+      *reinterpret_cast<uint2*>(pc + panel_offset16(r, (4 * c) & 63)) = make_uint2(pack_bf16x2(l.x, l.y), pack_bf16x2(l.z, l.w));
+      *reinterpret_cast<uint2*>(pc + panel_offset16(K + r, (4 * c) & 63)) = make_uint2(pack_bf16x2(h.x, h.y), pack_bf16x2(h.z, h.w));
+    } else {
+      *reinterpret_cast<float4*>(a_lo + o) = l;
+    }
   }
   for (int e = tid; e < K * (N / 4); e += 128) {
     const int r = e / (N / 4), c = e % (N / 4);
     const float4 v = *reinterpret_cast<const float4*>(B + (size_t)r * N + c * 4);
     float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    if (bf16c) h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
     const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
     if (!split) h = v;
     const uint32_t o = (uint32_t)(c >> 3) * panel + panel_chunk_offset_mn(r, c & 7);
     *reinterpret_cast<float4*>(b_hi + o) = h;
-    *reinterpret_cast<float4*>(b_lo + o) = l;
+    if (bf16c) {
+      unsigned char* pc = b_lo + (uint32_t)((4 * c) >> 6) * panel16;
+      *reinterpret_cast<uint2*>(pc + panel_offset16(r, (4 * c) & 63)) = make_uint2(pack_bf16x2(h.x, h.y), pack_bf16x2(h.z, h.w));
+      *reinterpret_cast<uint2*>(pc + panel_offset16(K + r, (4 * c) & 63)) = make_uint2(pack_bf16x2(l.x, l.y), pack_bf16x2(l.z, l.w));
+    } else {
+      *reinterpret_cast<float4*>(b_lo + o) = l;
+    }
   }
   fence_proxy_async();
   __syncthreads();
@@ -151,9 +186,17 @@ k_tc_selftest_mn(const float* __restrict__ A, const float* __restrict__ B, float
       const uint64_t dbh = make_smem_desc_mn(smem_u32(b_hi) + adv, panel);
       const uint64_t dbl = make_smem_desc_mn(smem_u32(b_lo) + adv, panel);
       mma_tf32(tmem, dah, dbh, idesc, j ? 1u : 0u);
-      if (split) {
+      if (split && !bf16c) {
         mma_tf32(tmem, dal, dbh, idesc, 1u);
         mma_tf32(tmem, dah, dbl, idesc, 1u);
+      }
+    }
+    if (bf16c) {   // [lo ; hi] x [hi ; lo]: 2K rows in steps of 16
+      const uint32_t idesc16 = make_idesc_bf16_mn(128, N);
+      for (int j = 0; j < 2 * K / 16; ++j) {
+        const uint32_t adv = (uint32_t)j * 2048u;
+        mma_bf16(tmem, make_smem_desc_mn16(smem_u32(a_lo) + adv, panel16), make_smem_desc_mn16(smem_u32(b_lo) + adv, panel16),
+                 idesc16, 1u);
       }
     }
     mma_commit(&done_bar);
@@ -178,7 +221,7 @@ extern "C" int conv3p_selftest_tc_mn(const float* A, const float* B, float* D, i
                                      conv3p_stream_t stream) {
   using namespace c3p;
   if (N < 32 || N > 256 || N % 32 || K < 8 || K > 64 || K % 8) return CONV3P_ERR_INVALID_ARGUMENT;
-  const size_t smem = 2 * (size_t)(4 + N / 32) * K * tc::PANEL_ROW_BYTES;
+  const size_t smem = 2 * (size_t)(4 + N / 32 + 1) * K * tc::PANEL_ROW_BYTES;
   { const int st_ = ensure_dynamic_smem(k_tc_selftest_mn, smem); if (st_) return st_; }
   k_tc_selftest_mn<<<1, 128, smem, stream>>>(A, B, D, N, K, split);
   C3P_LAUNCH_CHECK("k_tc_selftest_mn");

@@ -610,3 +610,32 @@ def test_backward_without_lists_is_an_error_status():
     assert L.conv3p_backward_f32(*args) == _lib.OK
     torch.cuda.synchronize()
     assert torch.isfinite(gi).all() and torch.isfinite(gf).all()
+
+
+@pytest.mark.parametrize("Cin,Cout", [(64, 128), (64, 64), (96, 32), (256, 256)])
+def test_bf16_correction_split_against_three_tf32_products(port, Cin, Cout):
+    """Tensor-core precision modes: the production split (TF32 main product + one BF16 chain for the two correction
+    terms) and plain 3xTF32 (engine flag 512) both meet the operator's tolerance against the float64 oracle; they are
+    different arithmetic (not bit-equal), and the production split stays within a small factor of 3xTF32's error."""
+    from pointwise_b200 import NeighborPlan, _lib, conv3p_backward, conv3p_forward
+    B, N = (1, 500) if Cin * Cout >= 65536 else (2, 1100)
+    pr = make_problem(B, N, Cin, Cout, "room", seed=41)
+    plan = NeighborPlan(dev(pr["points"]), 1, V).ensure_backward()
+    o32, o64, oabs = port.forward(pr["points"], pr["input"], pr["filter"], 1, V, with64=True)
+    r = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], 1, V, with64=True)
+    L = _lib.lib()
+    errs, outs = {}, {}
+    for flag in (0, 512):
+        prev = L.conv3p_set_engine(flag)
+        try:
+            y = conv3p_forward(plan, dev(pr["input"]), dev(pr["filter"])).cpu().numpy()
+            gi, gf = conv3p_backward(plan, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]))
+        finally:
+            L.conv3p_set_engine(prev)
+        errs[flag] = (assert_close_scaled(y, o64, oabs, RTOL, ATOL, f"forward[{flag}]"),
+                      assert_close_scaled(gi.cpu().numpy(), r[2], r[3], RTOL, ATOL, f"grad_input[{flag}]"),
+                      assert_close_scaled(gf.cpu().numpy(), r[4], r[5], RTOL, ATOL, f"grad_filter[{flag}]"))
+        outs[flag] = y
+    print("max err / sum|terms| (fwd, grad_input, grad_filter): production", errs[0], "3xTF32", errs[512])
+    assert not np.array_equal(outs[0], outs[512])
+    assert max(errs[0]) < 3e-6, errs          # 3x head-room under the 1e-5 tolerance
