@@ -227,6 +227,9 @@ int conv3p_set_engine(int engine);
  * Synchronise the device. */
 int conv3p_debug_phase_cycles(unsigned long long* host8);
 int conv3p_debug_cta_cycles(unsigned long long* host2);
+/* Same for the weight-gradient kernel (library variants built with -DC3P_W2_TIMED=1; zeros otherwise): 16 counters
+ * summed over all CTAs -- [0..7] phases of producer warp 0, [8..9] item loader, [10..13] MMA issuer. */
+int conv3p_debug_w2_cycles(unsigned long long* host16);
 
 /* Per-kernel timing for benchmarks: while enabled, every kernel launch is bracketed by CUDA events
  * on its stream.  conv3p_profile_enable(on) clears the records and returns the previous state.
@@ -244,6 +247,11 @@ int conv3p_selftest_tc(const float* A, const float* B, float* D, int N, int K, i
  * kernel): D[128,N] = A^T * B, A[K,128], B[K,N]; N % 32 == 0, K % 8 == 0, K <= 64. */
 int conv3p_selftest_tc_mn(const float* A, const float* B, float* D, int N, int K, int split,
                           conv3p_stream_t stream);
+
+/* Issue-rate probe of the tensor core (tools/mma_rate.py): one CTA issues reps x 8 tcgen05.mma with M = 128 and N
+ * columns and writes the elapsed SM cycles to cycles_device[0].  mode bit 0: MN-major operands (else K-major), bit 1:
+ * BF16 kind::f16 with K = 16 per instruction (else kind::tf32, K = 8). */
+int conv3p_debug_mma_rate(int N, int mode, int reps, unsigned long long* cycles_device, conv3p_stream_t stream);
 
 #ifdef __cplusplus
 }

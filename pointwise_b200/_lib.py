@@ -27,7 +27,7 @@ EXPORTS = [
     "conv3p_host_workspace_bytes", "conv3p_host_forward_f32", "conv3p_host_backward_f32",
     "conv3p_status_string", "conv3p_last_cuda_error", "conv3p_abi_version", "conv3p_launch_count",
     "conv3p_set_engine", "conv3p_profile_enable", "conv3p_profile_read",
-    "conv3p_selftest_tc", "conv3p_selftest_tc_mn", "conv3p_debug_phase_cycles", "conv3p_debug_cta_cycles",
+    "conv3p_selftest_tc", "conv3p_selftest_tc_mn", "conv3p_debug_phase_cycles", "conv3p_debug_cta_cycles", "conv3p_debug_w2_cycles", "conv3p_debug_mma_rate",
     "conv3p_augment_rotate_jitter_f32", "conv3p_xyz_sort_workspace_bytes", "conv3p_xyz_sort_f32",
 ]
 
@@ -101,6 +101,8 @@ def _declare(L):
     L.conv3p_profile_read.restype = ll
     L.conv3p_debug_phase_cycles.argtypes = [vp]
     L.conv3p_debug_cta_cycles.argtypes = [vp]
+    L.conv3p_debug_w2_cycles.argtypes = [vp]
+    L.conv3p_debug_mma_rate.argtypes = [i, i, i, vp, vp]
     L.conv3p_selftest_tc.argtypes = [vp, vp, vp, i, i, i, vp]
     L.conv3p_selftest_tc_mn.argtypes = [vp, vp, vp, i, i, i, vp]
     L.conv3p_augment_rotate_jitter_f32.argtypes = [vp, vp, vp, C.c_double, C.c_double, i, i, vp, vp]
@@ -115,7 +117,7 @@ def lib():
     if _lib is None:
         with _lock:
             if _lib is None:
-                path = _build.LIB_PATH
+                path = os.environ.get("CONV3P_LIB") or _build.LIB_PATH      # CONV3P_LIB: an experiment variant
                 if not os.path.exists(path):
                     try:
                         _build.build()

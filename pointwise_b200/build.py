@@ -27,15 +27,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """Compiles every .cu under csrc/ for sm_100a and links libconv3p_b200.so.  `defines` / `out` build an experiment
+    variant (compile-time switches such as -DC3P_W2_LOOK2=1) into another file, loaded with CONV3P_LIB=<path>
+    (tools/build_variants.py): A/B timing of whole libraries in one GPU call."""
+    lib_path = out or LIB_PATH
+    if not force and not out and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = LIB_DIR if not out else os.path.join(LIB_DIR, "obj_" + os.path.basename(out))
+    os.makedirs(obj_dir, exist_ok=True)
     objs = []
     procs = []
     for src in sources():
-        obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC, *ARCH_FLAGS, "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = [NVCC, *ARCH_FLAGS, "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", *[f"-D{d}" for d in defines],
                "-Xptxas", "-v" if verbose else "-warn-spills", "-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -48,12 +54,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [NVCC, *ARCH_FLAGS, "-shared", "-o", LIB_PATH, *objs]
-    out = subprocess.run(link, capture_output=True, text=True)
-    if out.returncode != 0:
-        print(out.stdout + out.stderr)
+    link = [NVCC, *ARCH_FLAGS, "-shared", "-o", lib_path, *objs]
+    res = subprocess.run(link, capture_output=True, text=True)
+    if res.returncode != 0:
+        print(res.stdout + res.stderr)
         raise RuntimeError("link failed")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -53,7 +53,13 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes) {
   std::lock_guard<std::mutex> lock(mu);
   size_t& have = done[std::make_pair(kernel, dev)];
   if (have >= bytes) return CONV3P_OK;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  // static + dynamic shared memory share the 227 KB a CTA may opt in to
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncGetAttributes");
+  const size_t limit = 227 * 1024 - fa.sharedSizeBytes;
+  if (bytes > limit) bytes = limit;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
   have = bytes;
   return CONV3P_OK;
@@ -91,7 +97,6 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, int S, long
 // involved, so the deferred overflow check never queues behind (or in front of) an application's bulk copies.
 __global__ void k_publish_header(const long long* __restrict__ header, volatile long long* host_out) {
   if (threadIdx.x < H_SLOTS) host_out[threadIdx.x] = header[threadIdx.x];
-  __threadfence_system();
 }
 
 int launch_reduce_partials(const float* partial, int S, long long nW, float* out, const long long* plan_header,

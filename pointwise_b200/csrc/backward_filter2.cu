@@ -18,6 +18,16 @@
 //
 // Warp roles: warps [0, NPW) producers (also the flush), NPW = MMA issuer + TMEM allocator, NPW+1 = item-list loader;
 // NPW = PTS / 4 (one quarter-warp per point of the tile).
+//
+// What bounds it (phase timers of C3P_W2_TIMED builds, tools/mma_rate.py, ncu; profiles/r2_summary.md): an M=128 x
+// N=64 tcgen05.mma occupies the tensor core for ~75 cycles whatever the operand layout or type (~43 cycles fixed +
+// N/2), so the 16 instructions of a 64-point stage take 1200 cycles -- the floor of this formulation, 0.46 ms at the
+// headline shape; on top of that the L1/shared-memory data pipe carries the operand reads of those MMAs (96 KB per
+// stage), the producers' panel stores (64 KB) and the row loads, ~1700 wavefront cycles per stage, and the producers
+// spend 40 % of their time queueing behind it when they issue the next stage's loads.  Measured and dropped: two
+// stages of register look-ahead (0.99 -> 1.08 ms), a ninth warp prefetching the G-store rows into L2 eight stages
+// ahead with cp.async.bulk.prefetch.L2 (0.87 -> 1.15 ms: the stall is not DRAM latency), 32-point tiles with a 4- or
+// 6-stage ring (1.56 ms), mbarrier waits without a suspend-time hint (no change).
 #include <cstdio>
 #include <cstdlib>
 #include <utility>
@@ -30,7 +40,19 @@ namespace c3p {
 
 using namespace tc;
 
-constexpr int W2_NIS = 4;      // item-list slots
+// Compile-time switch (tools/build_variants.py): C3P_W2_TIMED = 1 compiles in the phase timers of producer warp 0
+// (conv3p_debug_w2_cycles, tools/ab_backward.py).
+#ifndef C3P_W2_TIMED
+#define C3P_W2_TIMED 0
+#endif
+
+// cycles of producer warp 0, lane 0, summed over CTAs: items wait | first use of the prefetched rows | ring-slot wait |
+// split + stores + fence + arrive | input panels | flush | total
+// [8..15]: item loader: wait for a free item slot | total;  MMA issuer: wait input panels | wait G stage | wait flush | total
+__device__ unsigned long long w2_phase_cycles[16];
+
+constexpr int W2_NIS = 8;      // item-list slots
+constexpr int W2_MASKS = 1024; // cell masks of the CTA's tiles kept in shared memory (more tiles: read through L2)
 constexpr int W2_MAX_NGS = 6;  // G ring stages
 constexpr int W2_END = -1;
 
@@ -101,6 +123,10 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
       it_empty[W2_NIS], acc_full, acc_empty;
   __shared__ uint32_t tmem_slot;
   __shared__ int hdr[W2_NIS];   // accumulator | cell sub-mask << 8 | tile (CTA-local) << 12, or W2_END
+  // Cell masks of this CTA's tiles: every role walks them once per pass, the MMA issuer and the item-list loader
+  // with nothing to hide a global-load latency behind (measured: 36 % of the producers' time was spent waiting for
+  // item lists the loader had not requested yet).
+  __shared__ unsigned tile_mask[W2_MASKS];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long per_cta = (a.tiles + gridDim.x - 1) / gridDim.x;
@@ -130,10 +156,16 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
     __syncwarp();
     tmem_alloc(&tmem_slot, 512);
   }
+  for (long long t = tile_lo + tid; t < tile_hi && t - tile_lo < W2_MASKS; t += blockDim.x)
+    tile_mask[t - tile_lo] = __ldg(a.g_mask + t);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  auto cell_mask = [&](long long tile) -> unsigned {
+    const long long i = tile - tile_lo;
+    return i < W2_MASKS ? tile_mask[i] : __ldg(a.g_mask + tile);
+  };
 
   // mask of the pass's accumulators that have members in a tile with cell mask m (bit = accumulator - va0)
   auto pass_vas = [&](unsigned m, int va0, int va1) -> unsigned { return W2Map<GP>::pass_mask(m, va0, va1 - va0, mbs); };
@@ -143,13 +175,24 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
     // Quarter-warp q serves row q of the tile for the input panels and item (q + 4g) mod PTS of every cell of
     // stage g.
     const int q = warp * 4 + (lane >> 3), l8 = lane & 7;
+#if C3P_W2_TIMED
+    const bool timed = tid == 0;
+    long long tk = clock64();
+    const long long t_begin = tk;
+    unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define W2_PHASE(i) do { if (timed) { const long long t_ = clock64(); ph[i] += (unsigned long long)(t_ - tk); tk = t_; } } while (0)
+#else
+#define W2_PHASE(i) do { } while (0)
+#endif
     struct Stage {
       G2Item it[CS];
       int h;   // header of the stage
     };
     auto read_stage = [&](int g_, Stage& s) {
       const int slot = g_ & (W2_NIS - 1);
+      W2_PHASE(0);
       mbar_wait(&it_full[slot], (uint32_t)((g_ / W2_NIS) & 1));
+      W2_PHASE(7);
       s.h = hdr[slot];
       const unsigned sub = s.h == W2_END ? 0u : ((unsigned)s.h >> 8) & 15u;
 #pragma unroll
@@ -184,11 +227,14 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
     };
     int g_slot = 0, x_slot = 0;
     uint32_t g_wrap = 0, x_wrap = 0;   // completed trips around the G ring / the X buffers
-    // One stage of look-ahead: the next stage's items, with their first list ids (gather mode) or their G rows
-    // (store mode) in flight.  (Three stages were measured slower: register moves of loaded values stall like
-    // uses, and the extra registers spill.)
-    Stage ahead;
-    float4 ahead_rows[4];
+    // One stage of look-ahead in two STATIC register buffers (A for even stages, B for odd ones): the items of stage
+    // g + 1, with their first list ids (gather mode) or their G rows (store mode), are requested at the start of stage
+    // g.  Measured with the phase timers: the rows have arrived when they are needed (1 % of the producer time); two
+    // stages of look-ahead were slower (0.99 -> 1.08 ms), and so was a rotating register queue (moves of loaded values
+    // stall like uses).
+    Stage stA, stB;
+    float4 rowsA[4], rowsB[4];
+    bool odd_stage = false;
     int n_read = 0;
     bool ended = false;
     auto pull = [&](Stage& s, float4 (&r)[4]) {
@@ -202,19 +248,35 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
       ended = s.h == W2_END;
       if (FROM_STORE && !ended) fetch_rows(s, r);
     };
-    pull(ahead, ahead_rows);
+    pull(stA, rowsA);
+    W2_PHASE(0);
     for (int pass = 0; pass < npass; ++pass) {
       const int va0 = pass * FG, va1 = min(NVA, va0 + FG);
       unsigned pass_mask = 0;
-      int xrow = tile_lo < tile_hi ? __ldg(a.g_rowid + tile_lo * PTS + q) : -1;
-      unsigned mask_next = tile_lo < tile_hi ? pass_vas(__ldg(a.g_mask + tile_lo), va0, va1) : 0u;
+      // Input rows are requested one tile ahead and their row ids two tiles ahead (measured: loading them at the
+      // point of use cost a quarter of the producers' time, one exposed DRAM latency per tile visit and pass).
+      constexpr int XPRE = PTS == 64 ? 2 : 4;   // prefetched 32-channel panels of the row (the rest is loaded in place)
+      auto rid_at = [&](long long t) -> int { return t < tile_hi ? __ldg(a.g_rowid + t * PTS + q) : -1; };
+      float4 xv[XPRE];
+      auto x_request = [&](int rid) {
+        const float* xr = a.input + (size_t)(rid >= 0 ? rid : 0) * Cin + l8 * 4;
+#pragma unroll
+        for (int pnl = 0; pnl < XPRE; ++pnl)
+          xv[pnl] = (rid >= 0 && pnl < xp) ? ldg4(xr + pnl * PANEL_K) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      int rid0 = rid_at(tile_lo), rid1 = rid_at(tile_lo + 1);
+      x_request(rid0);
+      unsigned mask_next = tile_lo < tile_hi ? pass_vas(cell_mask(tile_lo), va0, va1) : 0u;
       for (long long tile = tile_lo; tile < tile_hi; ++tile) {
         const unsigned mask = mask_next;
-        const int row = xrow;
-        if (tile + 1 < tile_hi) {  // prefetch the next visit's row id and mask
-          xrow = __ldg(a.g_rowid + (tile + 1) * PTS + q);
-          mask_next = pass_vas(__ldg(a.g_mask + tile + 1), va0, va1);
-        }
+        const int row = rid0;
+        float4 xc[XPRE];
+#pragma unroll
+        for (int pnl = 0; pnl < XPRE; ++pnl) xc[pnl] = xv[pnl];
+        rid0 = rid1;
+        rid1 = rid_at(tile + 2);
+        x_request(rid0);
+        if (tile + 1 < tile_hi) mask_next = pass_vas(cell_mask(tile + 1), va0, va1);
         if (!mask) continue;
         pass_mask |= mask;
         // ---- input rows of the tile -> X panels (hi/lo) ---------------------------------------------------
@@ -224,29 +286,41 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
           if (++x_slot == NXB) { x_slot = 0; ++x_wrap; }
           unsigned char* xs = x_base + (size_t)xb * x_buf;
           const float* xr = a.input + (size_t)(row >= 0 ? row : 0) * Cin + l8 * 4;
-          for (int pnl = 0; pnl < xp; ++pnl) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row >= 0) v = ldg4(xr + pnl * PANEL_K);
+          auto x_store = [&](int pnl, const float4& v) {
             unsigned char* hi_dst = xs + (size_t)pnl * PANEL + panel_chunk_offset_mn(q, l8);
-            if (BF16C) {   // B side of the correction product: rows [0, PTS) hi, [PTS, 2 PTS) lo
+            if (BF16C) {   // B side of the correction product: rows [0, PTS) hi, [PTS, 2 PTS) lo (see the G stores)
               unsigned char* c = xs + x_half + (size_t)(pnl >> 1) * PANEL16;
               const int j = (pnl & 1) * 32 + 4 * l8;
               g2_store_split16(hi_dst, c + panel_offset16(PTS + q, j), c + panel_offset16(q, j), v);
             } else {
               g2_store_split(hi_dst, x_half, v);
             }
-          }
+          };
+#pragma unroll
+          for (int pnl = 0; pnl < XPRE; ++pnl)
+            if (pnl < xp) x_store(pnl, xc[pnl]);
+          for (int pnl = XPRE; pnl < xp; ++pnl)
+            x_store(pnl, row >= 0 ? ldg4(xr + pnl * PANEL_K) : make_float4(0.f, 0.f, 0.f, 0.f));
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&x_full[xb]);
+          W2_PHASE(4);
         }
         // ---- one G stage per active accumulator -----------------------------------------------------------
-        for (unsigned todo = mask; todo; todo &= todo - 1) {
-          Stage cur = ahead;
+        auto do_stage = [&](Stage& st_buf, float4 (&row_buf)[4], Stage& st_other, float4 (&row_other)[4]) {
+          const Stage cur = st_buf;
+          pull(st_other, row_other);     // stage g + 1 into the other buffer, before this one's rows are touched
+          W2_PHASE(0);
           float4 acc[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i] = ahead_rows[i];
-          pull(ahead, ahead_rows);
+          for (int i = 0; i < 4; ++i) acc[i] = row_buf[i];
+#if C3P_W2_TIMED
+          if (FROM_STORE) {   // force the arrival of the prefetched rows here so the wait is attributed to phase 1
+#pragma unroll
+            for (int i = 0; i < 4; ++i) asm volatile("" ::"f"(acc[i].x), "f"(acc[i].y), "f"(acc[i].z), "f"(acc[i].w));
+          }
+          W2_PHASE(1);
+#endif
           const int slot = g_slot;
           const uint32_t use = g_wrap;
           if (++g_slot == NGS) { g_slot = 0; ++g_wrap; }
@@ -254,25 +328,28 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
           bool waited = false;
 #pragma unroll
           for (int cs = 0; cs < CS; ++cs) {
+            G2Item item = cur.it[cs];
             if (!FROM_STORE) {
-              int nmax = max(cur.it[cs].n, __shfl_xor_sync(C3P_FULL_MASK, cur.it[cs].n, 8));
+              int nmax = max(item.n, __shfl_xor_sync(C3P_FULL_MASK, item.n, 8));
               nmax = max(nmax, __shfl_xor_sync(C3P_FULL_MASK, nmax, 16));
               const int ch0 = GP == 4 ? ((cur.h & 255) & ((1 << mbs) - 1)) * 128 : 0;
               float4 part[GP];
-              g2_gather<GP, 8 / GP, true>(part, cur.it[cs], nmax, a.grad_out, Cout, ch0, a.rows, a.weights, l8, max_row);
+              g2_gather<GP, 8 / GP, true>(part, item, nmax, a.grad_out, Cout, ch0, a.rows, a.weights, l8, max_row);
 #pragma unroll
               for (int kc = 0; kc < GP; ++kc) acc[cs * GP + kc] = part[kc];
             }
             if (!waited) {
               if (use >= 1) mbar_wait(&g_empty[slot], (use - 1) & 1u);
               waited = true;
+              W2_PHASE(2);
             }
-            const int p = cur.it[cs].p;
+            const int p = item.p;
             unsigned char* dst = stage + panel_chunk_offset_mn(p, l8);
 #pragma unroll
             for (int kc = 0; kc < GP; ++kc) {
               const int pi = cs * GP + kc;                  // 32-lane panel of the accumulator's M = 128
-              if (BF16C) {   // A side of the correction product: rows [0, PTS) lo, [PTS, 2 PTS) hi
+              if (BF16C) {
+                // A side of the correction product: rows [0, PTS) lo, [PTS, 2 PTS) hi
                 unsigned char* c = stage + g_half + (size_t)(pi >> 1) * PANEL16;
                 const int j = (pi & 1) * 32 + 4 * l8;
                 g2_store_split16(dst + (size_t)pi * PANEL, c + panel_offset16(p, j), c + panel_offset16(PTS + p, j), acc[pi]);
@@ -284,6 +361,11 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&g_full[slot]);
+          W2_PHASE(3);
+        };
+        for (unsigned todo = mask; todo; todo &= todo - 1) {
+          if (odd_stage) do_stage(stB, rowsB, stA, rowsA); else do_stage(stA, rowsA, stB, rowsB);
+          odd_stage = !odd_stage;
         }
       }
       // ---- flush this pass's accumulators: partial[cta][f][k][c] = D[lane(c), k] ----------------------------
@@ -316,52 +398,80 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty);
+      W2_PHASE(5);
     }
+#if C3P_W2_TIMED
+    if (timed) {
+      ph[6] = (unsigned long long)(clock64() - t_begin);
+      for (int i = 0; i < 8; ++i) atomicAdd(&w2_phase_cycles[i], ph[i]);
+    }
+#endif
   } else if (warp == NPW) {
     // =========================== MMA issuer (one thread) ===============================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32_mn(128, Cin), idesc16 = make_idesc_bf16_mn(128, Cin);
+      // descriptors of ring stage 0 / input buffer 0 (tc_common.cuh, Desc32): everything else is a 32-bit add
+      const Desc32 dg = split_desc(make_smem_desc_mn(smem_u32(g_base), PANEL));
+      const Desc32 dx = split_desc(make_smem_desc_mn(smem_u32(x_base), PANEL));
+      const Desc32 dg16 = split_desc(make_smem_desc_mn16(smem_u32(g_base) + g_half, PANEL16));
+      const Desc32 dx16 = split_desc(make_smem_desc_mn16(smem_u32(x_base) + x_half, PANEL16));
+      const uint32_t g_step = (2u * g_half) >> 4, x_step = x_buf >> 4, g_lo_off = g_half >> 4, x_lo_off = x_half >> 4;
       int g_slot = 0, x_slot = 0;
       uint32_t g_phase = 0, x_phase = 0;
+#if C3P_W2_TIMED
+      long long mk = clock64();
+      const long long m_begin = mk;
+      unsigned long long mph[3] = {0, 0, 0};
+#define W2_MPHASE(i) do { const long long t_ = clock64(); mph[i] += (unsigned long long)(t_ - mk); mk = t_; } while (0)
+#define W2_MTICK() do { mk = clock64(); } while (0)
+#else
+#define W2_MPHASE(i) do { } while (0)
+#define W2_MTICK() do { } while (0)
+#endif
       for (int pass = 0; pass < npass; ++pass) {
         const int va0 = pass * FG, va1 = min(NVA, va0 + FG);
         unsigned started = 0;
         if (pass > 0) {
+          W2_MTICK();
           mbar_wait(&acc_empty, (uint32_t)((pass - 1) & 1));
+          W2_MPHASE(2);
           tc_fence_after_sync();
         }
         for (long long tile = tile_lo; tile < tile_hi; ++tile) {
-          const unsigned mask = pass_vas(__ldg(a.g_mask + tile), va0, va1);
+          const unsigned mask = pass_vas(cell_mask(tile), va0, va1);
           if (!mask) continue;
           const int xb = x_slot;
+          W2_MTICK();
           mbar_wait(&x_full[xb], x_phase);
+          W2_MPHASE(0);
           if (++x_slot == NXB) { x_slot = 0; x_phase ^= 1u; }
-          const uint32_t x_hi = smem_u32(x_base + (size_t)xb * x_buf), x_lo = x_hi + x_half;
+          const uint32_t xw = dx.lo + (uint32_t)xb * x_step, xw16 = dx16.lo + (uint32_t)xb * x_step;
           const int ai_last = 31 - __clz(mask);
           for (unsigned todo = mask; todo; todo &= todo - 1) {
             const int ai = __ffs(todo) - 1;
             const int slot = g_slot;
+            W2_MTICK();
             mbar_wait(&g_full[slot], g_phase);
+            W2_MPHASE(1);
             if (++g_slot == NGS) { g_slot = 0; g_phase ^= 1u; }
             tc_fence_after_sync();
-            const uint32_t g_hi = smem_u32(g_base + (size_t)slot * 2 * g_half), g_lo = g_hi + g_half;
+            const uint32_t gw = dg.lo + (uint32_t)slot * g_step, gw16 = dg16.lo + (uint32_t)slot * g_step;
             const uint32_t d = tmem + (uint32_t)(ai * Cin);
+            const uint32_t first = (started >> ai) & 1u;
 #pragma unroll
-            for (int j = 0; j < PTS / 8; ++j) {
-              const uint32_t adv = (uint32_t)j * 1024u;  // 8 points further down the panels
-              const uint64_t dgh = make_smem_desc_mn(g_hi + adv, PANEL), dgl = make_smem_desc_mn(g_lo + adv, PANEL);
-              const uint64_t dxh = make_smem_desc_mn(x_hi + adv, PANEL), dxl = make_smem_desc_mn(x_lo + adv, PANEL);
-              mma_tf32(d, dgh, dxh, idesc, (((started >> ai) & 1u) | (unsigned)j) ? 1u : 0u);
+            for (int j = 0; j < PTS / 8; ++j) {          // 8 points (1 KB of every panel) per TF32 instruction
+              const uint32_t adv = (uint32_t)j * 64u;
+              mma_tf32(d, gw + adv, dg.hi, xw + adv, dx.hi, idesc, j ? 1u : first);
               if (!BF16C) {
-                mma_tf32(d, dgl, dxh, idesc, 1u);
-                mma_tf32(d, dgh, dxl, idesc, 1u);
+                mma_tf32(d, gw + g_lo_off + adv, dg.hi, xw + adv, dx.hi, idesc, 1u);
+                mma_tf32(d, gw + adv, dg.hi, xw + x_lo_off + adv, dx.hi, idesc, 1u);
               }
             }
-            if (BF16C) {   // [G_lo ; G_hi]^T x [X_hi ; X_lo]: 2 * PTS rows in steps of 16
+            if (BF16C) {   // [G_lo ; G_hi]^T x [X_hi ; X_lo]: 2 * PTS rows in steps of 16 (2 KB of every panel)
 #pragma unroll
               for (int j = 0; j < PTS / 8; ++j) {
-                const uint32_t adv = (uint32_t)j * 2048u;
-                mma_bf16(d, make_smem_desc_mn16(g_lo + adv, PANEL16), make_smem_desc_mn16(x_lo + adv, PANEL16), idesc16, 1u);
+                const uint32_t adv = (uint32_t)j * 128u;
+                mma_bf16(d, gw16 + adv, dg16.hi, xw16 + adv, dx16.hi, idesc16, 1u);
               }
             }
             started |= 1u << ai;
@@ -371,20 +481,36 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
         }
         mma_commit(&acc_full);
       }
+#if C3P_W2_TIMED
+      atomicAdd(&w2_phase_cycles[10], mph[0]);
+      atomicAdd(&w2_phase_cycles[11], mph[1]);
+      atomicAdd(&w2_phase_cycles[12], mph[2]);
+      atomicAdd(&w2_phase_cycles[13], (unsigned long long)(clock64() - m_begin));
+#endif
     }
   } else {
     // =========================== item-list loader (one thread) ==========================================
     if (lane == 0) {
       int g = 0;
+#if C3P_W2_TIMED
+      const long long l_begin = clock64();
+      unsigned long long l_wait = 0;
+#endif
       for (int pass = 0; pass < npass; ++pass) {
         const int va0 = pass * FG, va1 = min(NVA, va0 + FG);
         for (long long tile = tile_lo; tile < tile_hi; ++tile) {
-          const unsigned cellmask = __ldg(a.g_mask + tile);
+          const unsigned cellmask = cell_mask(tile);
           for (unsigned todo = pass_vas(cellmask, va0, va1); todo; todo &= todo - 1) {
             const int va = va0 + __ffs(todo) - 1;
             const unsigned sub = W2Map<GP>::cells(cellmask, va, mbs);
             const int slot = g & (W2_NIS - 1), use = g / W2_NIS;
+#if C3P_W2_TIMED
+            const long long lw = clock64();
+#endif
             if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
+#if C3P_W2_TIMED
+            l_wait += (unsigned long long)(clock64() - lw);
+#endif
             hdr[slot] = va | ((int)sub << 8) | ((int)(tile - tile_lo) << 12);
             mbar_arrive_expect_tx(&it_full[slot], (uint32_t)__popc(sub) * PTS * (uint32_t)sizeof(uint2));
 #pragma unroll
@@ -402,6 +528,10 @@ __global__ void __launch_bounds__((PTS / 4 + 2) * 32, 1) k_backward_filter2(cons
       if (use >= 1) mbar_wait(&it_empty[slot], (uint32_t)((use - 1) & 1));
       hdr[slot] = W2_END;
       mbar_arrive(&it_full[slot]);
+#if C3P_W2_TIMED
+      atomicAdd(&w2_phase_cycles[8], l_wait);
+      atomicAdd(&w2_phase_cycles[9], (unsigned long long)(clock64() - l_begin));
+#endif
     }
   }
   tc_fence_before_sync();
@@ -430,7 +560,7 @@ static bool w2_config(int N, long long capacity, int Cin, int Cout, W2Config* c)
     }
     return r;
   }();
-  const size_t budget = 227 * 1024 - 1024;
+  const size_t budget = 227 * 1024 - 1024 - W2_MASKS * sizeof(unsigned);   // static: barriers, headers, tile masks
   const int CS = 4 / c->GP;
   // preference: 64-point tiles with two input buffers; else 32-point tiles (two input buffers, deeper ring); else a
   // single input buffer
@@ -475,7 +605,7 @@ size_t backward_filter2_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout)
 template <bool FROM_STORE, int GP, int PTS, bool BF16C>
 static int w2_launch(const W2Args& a, int grid, size_t smem, cudaStream_t stream) {
   auto kern = k_backward_filter2<FROM_STORE, GP, PTS, BF16C>;
-  const int st = ensure_dynamic_smem(kern, 227 * 1024 - 1024);
+  const int st = ensure_dynamic_smem(kern, 227 * 1024);   // granted: 227 KB minus the kernel's static shared memory
   if (st) return st;
   {
     LaunchTimer timer_("k_backward_filter_tc", stream);
@@ -529,3 +659,12 @@ int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const flo
 }
 
 }  // namespace c3p
+
+// profiling helper (C3P_W2_TIMED builds): read and clear the phase timers of k_backward_filter2
+extern "C" int conv3p_debug_w2_cycles(unsigned long long* host16) {
+  unsigned long long* host8 = host16;
+  unsigned long long zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(host8, c3p::w2_phase_cycles, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;
+  if (cudaMemcpyToSymbol(c3p::w2_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return CONV3P_ERR_CUDA;
+  return CONV3P_OK;
+}

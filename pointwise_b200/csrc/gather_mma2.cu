@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
         auto store_row = [&](int p, const float4 (&v)[NKC]) {
           const uint32_t o = panel_chunk_offset(p, l8);
           if (BF16C) {
+            // correction panel row = [lo (32 ch) | hi (32 ch)]
             const uint32_t oc = 128 * PANEL_ROW_BYTES + (uint32_t)p * PANEL_ROW_BYTES + ((uint32_t)(l8 & 1) << 3);
             const uint32_t c_lo = oc + ((((uint32_t)l8 >> 1) ^ ((uint32_t)p & 7u)) << 4);
             const uint32_t c_hi = oc + (((4u + ((uint32_t)l8 >> 1)) ^ ((uint32_t)p & 7u)) << 4);
@@ -450,9 +451,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
       // a weight panel is needed 512 MMA cycles after its hi half and the hi unit is released before the lo unit.
       if (lane == 0) {
         const uint32_t idesc = make_idesc_tf32(128, Nout), idesc16 = make_idesc_bf16(128, Nout);
-        const uint64_t a_desc0 = make_smem_desc(s_a), w_desc0 = make_smem_desc(s_w);
-        const uint64_t a_lo_off = (uint64_t)((128 * PANEL_ROW_BYTES) >> 4);
-        const uint64_t a_step = (uint64_t)(G2_A_STAGE >> 4), w_step = (uint64_t)(unit_bytes >> 4);
+        // descriptors of ring stage 0 / weight unit 0 (tc_common.cuh, Desc32): everything else is a 32-bit add
+        const Desc32 da = split_desc(make_smem_desc(s_a)), dw = split_desc(make_smem_desc(s_w));
+        const uint32_t a_lo_off = (uint32_t)((128 * PANEL_ROW_BYTES) >> 4);
+        const uint32_t a_step = (uint32_t)(G2_A_STAGE >> 4), w_step = unit_bytes >> 4;
         unsigned started = 0;
         for (int f = 0; f < C3P_NCELL; ++f) {
           const unsigned act = active[f];
@@ -476,14 +478,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
                 if (t == t_first) mbar_wait(bar(G2B_W_FULL, us[2 * kc]), up[2 * kc]);
                 mbar_wait(bar(G2B_A_FULL, m_aslot), m_aphase);
                 tc_fence_after_sync();
-                const uint64_t dah = a_desc0 + (uint64_t)m_aslot * a_step, dal = dah + a_lo_off;
-                const uint64_t dwh = w_desc0 + (uint64_t)us[2 * kc] * w_step;
-                const uint64_t dwl = w_desc0 + (uint64_t)us[2 * kc + 1] * w_step;
+                const uint32_t ah = da.lo + (uint32_t)m_aslot * a_step, al = ah + a_lo_off;
+                const uint32_t wh = dw.lo + (uint32_t)us[2 * kc] * w_step, wl = dw.lo + (uint32_t)us[2 * kc + 1] * w_step;
 #pragma unroll
                 for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
-                  const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
-                  mma_tf32(d, dah + adv, dwh + adv, idesc, acc_flag);
-                  if (!BF16C) mma_tf32(d, dal + adv, dwh + adv, idesc, 1u);
+                  const uint32_t adv = (uint32_t)((ks * UMMA_K * 4) >> 4);
+                  mma_tf32(d, ah + adv, da.hi, wh + adv, dw.hi, idesc, acc_flag);
+                  if (!BF16C) mma_tf32(d, al + adv, da.hi, wh + adv, dw.hi, idesc, 1u);
                   acc_flag = 1u;
                 }
                 if (t == t_last) mma_commit(bar(G2B_W_EMPTY, us[2 * kc]));
@@ -493,10 +494,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
                 }
 #pragma unroll
                 for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
-                  const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
+                  const uint32_t adv = (uint32_t)((ks * UMMA_K * 4) >> 4);
                   // BF16C: [A_lo | A_hi] x [W_hi | W_lo], 64 bf16 of K in 4 steps of 16 (32 bytes each, like TF32's 8 x 4)
-                  if (BF16C) mma_bf16(d, dal + adv, dwl + adv, idesc16, 1u);
-                  else mma_tf32(d, dah + adv, dwl + adv, idesc, 1u);
+                  if (BF16C) mma_bf16(d, al + adv, da.hi, wl + adv, dw.hi, idesc16, 1u);
+                  else mma_tf32(d, ah + adv, da.hi, wl + adv, dw.hi, idesc, 1u);
                 }
                 mma_commit(bar(G2B_A_EMPTY, m_aslot));
                 if (t == t_last) mma_commit(bar(G2B_W_EMPTY, us[2 * kc + 1]));
@@ -704,7 +705,7 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
   const int sms = sm_count();
   const long long tiles = subtiles < sms ? subtiles : sms;  // persistent CTAs, one per SM
   auto launch = [&](auto kern) -> int {
-    const int st_ = ensure_dynamic_smem(kern, 227 * 1024 - 2048);   // once per (kernel, device)
+    const int st_ = ensure_dynamic_smem(kern, 227 * 1024);   // once per (kernel, device); granted minus static shared memory
     if (st_) return st_;
     {
       LaunchTimer timer_(name, stream);

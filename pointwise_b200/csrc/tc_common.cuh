@@ -115,6 +115,8 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
 }
 
 // ---- mbarrier ---------------------------------------------------------------------------------------
+// try_wait with a suspend-time hint: the thread may sleep until the phase completes (measured: same speed without)
+#define C3P_TRY_WAIT "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x4E20;\n\t"
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -133,7 +135,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x4E20;\n\t"
+      C3P_TRY_WAIT
       "@P1 bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
@@ -161,7 +163,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x4E20;\n\t"
+      C3P_TRY_WAIT
       "@P1 bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
@@ -252,6 +254,44 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same with the descriptors as (low word, high word) pairs.  One thread issues every MMA of a CTA; measured with
+// tools/mma_rate.py, an M=128 x N=64 instruction occupies the tensor core for ~43 cycles, so the issuing thread has
+// only ~10 dependent instructions per MMA before IT becomes the bottleneck (64-bit descriptor arithmetic per MMA cost
+// ~90 cycles each in the weight-gradient kernel).  The address field is the low 14 bits of the low word (bytes >> 4);
+// stepping through a panel or a ring is a 32-bit add on that word that can never carry out of the field (shared
+// memory addresses are < 256 KB), the high word is constant per operand.
+struct Desc32 {
+  uint32_t lo, hi;
+};
+__device__ __forceinline__ Desc32 split_desc(uint64_t d) { return Desc32{(uint32_t)d, (uint32_t)(d >> 32)}; }
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // All previously issued tcgen05.mma of this thread arrive on `bar` when they complete (implies

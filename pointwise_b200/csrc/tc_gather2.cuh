@@ -83,8 +83,12 @@ __device__ __forceinline__ void g2_store_split(uint32_t dst, uint32_t lo_offset,
   sts128(dst + lo_offset, make_float4(l0.x, l0.y, l1.x, l1.y));
 }
 
-// TF32 main panel + BF16 correction panel (tc_common.cuh, "BF16 correction products"): writes hi = tf32_rn(v) as fp32
-// at `hi_dst` and the BF16 pairs of lo = v - hi and of hi (8 bytes each) at `lo16_dst` / `hi16_dst`.
+// TF32 main panel + BF16 correction panel (tc_common.cuh, "BF16 correction products").  A lane owns 4 channels of its
+// row: hi = tf32_rn(v) goes to the fp32 panel as one 16-byte chunk, the BF16 pieces of lo and hi are 8 bytes each.
+// (A lane-pair exchange that turns the two 8-byte stores into one conflict-free 16-byte store per lane was measured:
+// grad_input 1.52 -> 1.62 ms -- the shuffles and selects cost the producers more than the bank conflicts.)
+// hi = tf32_rn(v) as one fp32 chunk at `hi_dst`; the BF16 pairs of lo = v - hi and of hi (8 bytes each) at `lo16_dst`
+// and `hi16_dst`.
 __device__ __forceinline__ void g2_store_split16(uint32_t hi_dst, uint32_t lo16_dst, uint32_t hi16_dst, const float4& v) {
   const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
   const float2 l0 = __fadd2_rn(make_float2(v.x, v.y), make_float2(-h.x, -h.y));

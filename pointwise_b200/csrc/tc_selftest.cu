@@ -215,7 +215,70 @@ k_tc_selftest_mn(const float* __restrict__ A, const float* __restrict__ B, float
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// Issue-rate probe: one CTA issues `reps` rounds of 8 tcgen05.mma (M = 128, N columns, operands at fixed shared-memory
+// addresses: contents irrelevant) and measures the cycles until the last one has completed.  mode bit 0: MN-major
+// operands (else K-major); bit 1: kind::f16 BF16 (K = 16 per instruction) instead of kind::tf32 (K = 8).
+__global__ void __launch_bounds__(128, 1) k_mma_rate(int N, int mode, int reps, unsigned long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 * 1024) / 16; i += 128) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid == 0) {
+    mbar_init(&done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const bool mn = mode & 1, bf = mode & 2;
+    const uint32_t a0 = smem_u32(smem), b0 = a0 + 32 * 1024;          // A: 4 panels of 64 rows, B: up to 8 panels of 32 rows
+    const uint32_t idesc = bf ? (mn ? make_idesc_bf16_mn(128, N) : make_idesc_bf16(128, N))
+                              : (mn ? make_idesc_tf32_mn(128, N) : make_idesc_tf32(128, N));
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint64_t da, db;
+        if (!mn) {          // K-major: panels of [rows x 128 B], 32 bytes of K per step (4 steps per panel)
+          da = make_smem_desc(a0 + (uint32_t)(j >> 2) * 16384u) + (uint64_t)((j & 3) * 2);
+          db = make_smem_desc(b0 + (uint32_t)(j >> 2) * (uint32_t)N * 128u) + (uint64_t)((j & 3) * 2);
+        } else if (!bf) {   // MN-major fp32: 8 rows (1 KB) per step, 32-wide MN blocks 8 KB (A) / 4 KB (B) apart
+          da = make_smem_desc_mn(a0 + (uint32_t)j * 1024u, 8192u);
+          db = make_smem_desc_mn(b0 + (uint32_t)(j & 3) * 1024u, 4096u);
+        } else {            // MN-major bf16: 16 rows (2 KB) per step, 64-wide MN blocks 16 KB (A) / 8 KB (B) apart
+          da = make_smem_desc_mn16(a0 + (uint32_t)j * 2048u, 16384u);
+          db = make_smem_desc_mn16(b0 + (uint32_t)(j & 3) * 2048u, 8192u);
+        }
+        if (bf) mma_bf16(tmem, da, db, idesc, (r | j) ? 1u : 0u);
+        else mma_tf32(tmem, da, db, idesc, (r | j) ? 1u : 0u);
+      }
+    }
+    mma_commit(&done_bar);
+    mbar_wait(&done_bar, 0);
+    out[0] = (unsigned long long)(clock64() - t0);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace c3p
+
+extern "C" int conv3p_debug_mma_rate(int N, int mode, int reps, unsigned long long* cycles_device,
+                                     conv3p_stream_t stream) {
+  using namespace c3p;
+  if (N < 16 || N > 256 || N % 16 || reps < 1 || !cycles_device) return CONV3P_ERR_INVALID_ARGUMENT;
+  const size_t smem = 128 * 1024;
+  { const int st_ = ensure_dynamic_smem(k_mma_rate, smem); if (st_) return st_; }
+  k_mma_rate<<<1, 128, smem, stream>>>(N, mode, reps, cycles_device);
+  C3P_LAUNCH_CHECK("k_mma_rate");
+  return CONV3P_OK;
+}
 
 extern "C" int conv3p_selftest_tc_mn(const float* A, const float* B, float* D, int N, int K, int split,
                                      conv3p_stream_t stream) {

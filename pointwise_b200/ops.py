@@ -104,8 +104,8 @@ PREFETCH_BACKWARD = os.environ.get("CONV3P_PREFETCH_BACKWARD", "1") != "0"
 _side_streams = {}
 
 
-def _side_stream(device) -> torch.cuda.Stream:
-    key = torch.device(device).index
+def _side_stream(device, role: str = "lists") -> torch.cuda.Stream:
+    key = (torch.device(device).index, role)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device)
     return _side_streams[key]
@@ -259,12 +259,19 @@ class NeighborPlan:
     def _enqueue_header_copy(self) -> None:
         import weakref
         self._stats_slot = _StatsSlots.take()
+        # On its own stream, ordered after the plan build only: the store into host memory crosses PCIe and may sit
+        # behind an application's bulk device->host copies; nothing on the compute stream ever waits for it.
+        built = torch.cuda.Event()
+        built.record(torch.cuda.current_stream(self.device))
+        side = _side_stream(self.device, "stats")
+        side.wait_event(built)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().conv3p_plan_publish_stats(self.geom, _ptr(self.buffer),
                                                             C.c_void_p(self._stats_slot.data_ptr()),
-                                                            _stream_ptr(self.device)))
+                                                            C.c_void_p(side.cuda_stream)))
         self._stats_event = torch.cuda.Event()
-        self._stats_event.record(torch.cuda.current_stream(self.device))
+        self._stats_event.record(side)
+        self.buffer.record_stream(side)
         _pending_checks.append(weakref.ref(self))
 
     def __del__(self):
