@@ -565,9 +565,6 @@ def gpu_arm(args):
     device = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa(local_rank) if world > 1 else {"bound": False, "why": "single rank"}
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     if args.workload in NETS:
         return net_arm(args, rank, world, device)
@@ -826,6 +823,11 @@ def main():
         reference_arm(args)
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) and any other NCCL log line go
+    # to stderr.  Set before torch / NCCL are loaded.
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun when called directly with --gpus N
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
