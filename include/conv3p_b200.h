@@ -84,6 +84,8 @@ typedef struct {
   size_t bwd_row;      /* int32[capacity] rows b*N+ii                                       */
   size_t bwd_weight;   /* float[capacity] 1/count(ii, f')                                   */
   size_t sort_tmp;     /* scratch of the radix sort                                         */
+  size_t cell_start;   /* uint32[B][cell_cap+1] bin offsets: first sorted position of every voxel-grid cell (lower
+                          bound), cell_cap = clamp(16*N, 4096, 65536); clouds with more cells search by bisection */
   size_t total_bytes;
 } conv3p_plan_layout_t;
 

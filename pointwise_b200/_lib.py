@@ -45,7 +45,7 @@ class PlanStats(C.Structure):
 class PlanLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
         "header", "cloud_meta", "sorted_key", "sorted_xyzi", "count_table", "pair_begin", "pair_len",
-        "pair_row", "bwd_count", "bwd_row", "bwd_weight", "sort_tmp", "total_bytes")]
+        "pair_row", "bwd_count", "bwd_row", "bwd_weight", "sort_tmp", "cell_start", "total_bytes")]
 
 
 class Conv3pError(RuntimeError):

@@ -179,6 +179,7 @@ int compute_layout(const conv3p_geom_t* g, conv3p_plan_layout_t* L) {
   L->bwd_row = take(sizeof(int) * cap);
   L->bwd_weight = take(sizeof(float) * cap);
   L->sort_tmp = take(sizeof(uint32_t) * 4 * pts);
+  L->cell_start = take(sizeof(uint32_t) * (size_t)g->B * ((size_t)cell_cap(g->N) + 1));
   L->total_bytes = o;
   return CONV3P_OK;
 }
@@ -202,6 +203,8 @@ int make_view(const conv3p_geom_t* g, const void* plan, size_t plan_bytes, PlanV
   v->bwd_row = reinterpret_cast<int*>(p + L.bwd_row);
   v->bwd_weight = reinterpret_cast<float*>(p + L.bwd_weight);
   v->sort_tmp = reinterpret_cast<uint32_t*>(p + L.sort_tmp);
+  v->cell_start = reinterpret_cast<uint32_t*>(p + L.cell_start);
+  v->cell_cap = cell_cap(g->N);
   return CONV3P_OK;
 }
 

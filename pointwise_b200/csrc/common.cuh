@@ -24,6 +24,8 @@ struct PlanView {
   int* bwd_row;
   float* bwd_weight;
   uint32_t* sort_tmp;
+  uint32_t* cell_start;   // [B][cell_cap + 1] bin offsets of the voxel grid (k_cloud_sort), see cell_cap()
+  int cell_cap;
 };
 
 namespace c3p {
@@ -39,6 +41,12 @@ struct RowIO {
 };
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+// Cells of the per-cloud bin-offset table: enough for the clouds of the reference's data at voxel 0.1 (a [-1,1]^3
+// shape has 22^3 = 10,648 cells, an S3DIS block 12 x 12 x 32 = 4,608); a cloud with more cells falls back to bisection.
+inline int cell_cap(int N) {
+  const long long c = 16LL * N;
+  return (int)(c < 4096 ? 4096 : (c > 65536 ? 65536 : c));
+}
 
 int compute_layout(const conv3p_geom_t* g, conv3p_plan_layout_t* L);
 int make_view(const conv3p_geom_t* g, const void* plan, size_t plan_bytes, PlanView* v);

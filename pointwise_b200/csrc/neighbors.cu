@@ -85,9 +85,13 @@ struct Query {
 
 // Visits every candidate of the query's window; calls fn(f, j) warp-collectively with f = kernel
 // cell 0..26 of an accepted neighbour (or -1) and j its index inside the cloud.
+// `bins` = the cloud's bin-offset table (k_cloud_sort: first sorted position of every grid cell, nullptr for a cloud
+// with more cells than the table holds): a run of cells of one grid row is then two table reads instead of two
+// bisections of the sorted keys.
 template <typename Fn>
 __device__ __forceinline__ void sweep(const Query& q, const uint32_t* __restrict__ keys,
-                                      const float4* __restrict__ cand, int N, int lane, Fn fn) {
+                                      const uint32_t* __restrict__ bins, const float4* __restrict__ cand, int N,
+                                      int lane, Fn fn) {
   const int nrows = q.wz.cells * q.wy.cells;
   const int nseg = nrows * q.wx.n;
   for (int s0 = 0; s0 < nseg; s0 += 32) {
@@ -103,8 +107,13 @@ __device__ __forceinline__ void sweep(const Query& q, const uint32_t* __restrict
       const int cy = window_cell(q.wy, r - rz * q.wy.cells);
       const int cz = window_cell(q.wz, rz);
       const uint32_t rowkey = (uint32_t)((cz * q.dimy + cy) * q.dimx);
-      start = lower_bound_key(keys, N, rowkey + (uint32_t)q.wx.lo[xr]);
-      len = lower_bound_key(keys, N, rowkey + (uint32_t)q.wx.hi[xr] + 1u) - start;
+      if (bins) {
+        start = (int)__ldg(bins + rowkey + (uint32_t)q.wx.lo[xr]);
+        len = (int)__ldg(bins + rowkey + (uint32_t)q.wx.hi[xr] + 1u) - start;
+      } else {
+        start = lower_bound_key(keys, N, rowkey + (uint32_t)q.wx.lo[xr]);
+        len = lower_bound_key(keys, N, rowkey + (uint32_t)q.wx.hi[xr] + 1u) - start;
+      }
     }
     int incl = len;
 #pragma unroll
@@ -133,9 +142,10 @@ __device__ __forceinline__ void sweep(const Query& q, const uint32_t* __restrict
         // closed box, tf_conv3p_atrous.cpp:277
         if (!(c.x < q.lo[0] || c.x > q.hi[0] || c.y < q.lo[1] || c.y > q.hi[1] ||
               c.z < q.lo[2] || c.z > q.hi[2])) {
-          int tx = tap_of(c.x, q.lo[0], q.voxel, q.full[0], q.stride[0]);
-          int ty = tap_of(c.y, q.lo[1], q.voxel, q.full[1], q.stride[1]);
-          int tz = tap_of(c.z, q.lo[2], q.voxel, q.full[2], q.stride[2]);
+          // (tap_of_fast: bit-identical to the IEEE divide of :280-282, see common.cuh)
+          int tx = tap_of_fast(c.x, q.lo[0], q.voxel, q.inv_voxel, q.full[0], q.stride[0]);
+          int ty = tap_of_fast(c.y, q.lo[1], q.voxel, q.inv_voxel, q.full[1], q.stride[1]);
+          int tz = tap_of_fast(c.z, q.lo[2], q.voxel, q.inv_voxel, q.full[2], q.stride[2]);
           if ((tx | ty | tz) >= 0) f = (tz * 3 + ty) * 3 + tx;  // :290
         }
       }
@@ -164,6 +174,7 @@ __global__ void __launch_bounds__(NB_THREADS)
 k_neighbor_search(int B, int N, int sx_, int sy_, int sz_, float voxel, long long capacity, PlanView v) {
   const int sx = S ? S : sx_, sy = S ? S : sy_, sz = S ? S : sz_;
   __shared__ uint32_t stash[NB_WARPS][STASH_CAP];
+  __shared__ uint16_t stash_rank[NB_WARPS][STASH_CAP];   // position of the pair among its cell's members (visiting order)
   __shared__ int wcnt[NB_WARPS][32];
   __shared__ int wpre[NB_WARPS][32];
   __shared__ int wrun[NB_WARPS][32];
@@ -176,6 +187,7 @@ k_neighbor_search(int B, int N, int sx_, int sy_, int sz_, float voxel, long lon
   const float vmin[3] = {meta[0], meta[1], meta[2]};
   const int dim[3] = {__float_as_int(meta[4]), __float_as_int(meta[5]), __float_as_int(meta[6])};
   const uint32_t* keys = v.sorted_key + (size_t)b * N;
+  const uint32_t* bins = (__float_as_int(meta[7]) & 256) ? v.cell_start + (size_t)b * ((size_t)v.cell_cap + 1) : nullptr;
   const float4* cand = v.sorted_xyzi + (size_t)b * N;
   const float4 me = v.sorted_xyzi[qpos];
   const size_t row = (size_t)b * N + __float_as_int(me.w);
@@ -201,18 +213,31 @@ k_neighbor_search(int B, int N, int sx_, int sy_, int sz_, float voxel, long lon
   int* pre = wpre[warp];
   int* run = wrun[warp];
   uint32_t* st = stash[warp];
+  uint16_t* sr = stash_rank[warp];
   cnt[lane] = 0;
   run[lane] = 0;
   __syncwarp();
 
-  // pass 1: count per cell, keep the first STASH_CAP pairs in shared memory
+  // pass 1: count per cell, keep the first STASH_CAP pairs in shared memory together with their rank inside their
+  // cell (members of a cell keep visiting order): one match per chunk instead of a shared-memory atomic per pair
+  // here and a second match per pair when the list is written
   int found = 0;
-  sweep(q, keys, cand, N, lane, [&](int f, int j) {
-    const unsigned hits = __ballot_sync(C3P_FULL_MASK, f >= 0);
-    if (f >= 0) {
+  sweep(q, keys, bins, cand, N, lane, [&](int f, int j) {
+    const bool hit = f >= 0;
+    const unsigned hits = __ballot_sync(C3P_FULL_MASK, hit);
+    const unsigned peers = __match_any_sync(C3P_FULL_MASK, hit ? f : C3P_NCELL);
+    const unsigned before = peers & lanemask_lt();
+    int rank = 0;
+    if (hit) rank = cnt[f] + __popc(before);
+    __syncwarp();
+    if (hit && before == 0u) cnt[f] += __popc(peers);
+    __syncwarp();
+    if (hit) {
       const int slot = found + __popc(hits & lanemask_lt());
-      if (slot < STASH_CAP) st[slot] = (uint32_t)j | ((uint32_t)f << 27);
-      atomicAdd(&cnt[f], 1);
+      if (slot < STASH_CAP) {
+        st[slot] = (uint32_t)j | ((uint32_t)f << 27);
+        sr[slot] = (uint16_t)rank;
+      }
     }
     found += __popc(hits);
   });
@@ -243,14 +268,12 @@ k_neighbor_search(int B, int N, int sx_, int sy_, int sz_, float voxel, long lon
   int* out = v.pair_row + begin;
   const int rowbase = b * N;
   if (K <= STASH_CAP) {
-    for (int c = 0; c < K; c += 32) {
-      const bool valid = c + lane < K;
-      const uint32_t e = valid ? st[c + lane] : 0u;
-      const int slot = place(valid, (int)(e >> 27), pre, run);
-      if (valid) out[slot] = rowbase + (int)(e & J_MASK);
+    for (int c = lane; c < K; c += 32) {
+      const uint32_t e = st[c];
+      out[pre[e >> 27] + (int)sr[c]] = rowbase + (int)(e & J_MASK);
     }
   } else {  // pass 2 for very dense neighbourhoods: same visiting order, placed directly
-    sweep(q, keys, cand, N, lane, [&](int f, int j) {
+    sweep(q, keys, bins, cand, N, lane, [&](int f, int j) {
       const int slot = place(f >= 0, f, pre, run);
       if (f >= 0) out[slot] = rowbase + j;
     });

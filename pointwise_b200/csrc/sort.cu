@@ -17,7 +17,7 @@ constexpr int MAX_DIM = 1024;
 __global__ void __launch_bounds__(SORT_THREADS)
 k_cloud_sort(const float* __restrict__ points, int N, float voxel, float* __restrict__ cloud_meta,
              uint32_t* __restrict__ sorted_key, float4* __restrict__ sorted_xyzi,
-             uint32_t* __restrict__ tmp) {
+             uint32_t* __restrict__ tmp, uint32_t* __restrict__ cell_start, int cell_cap) {
   __shared__ float red[6][SORT_WARPS];
   __shared__ float box[6];
   __shared__ uint32_t base[256];
@@ -72,11 +72,12 @@ k_cloud_sort(const float* __restrict__ points, int N, float voxel, float* __rest
   }
   const uint32_t cells = (uint32_t)dim[0] * dim[1] * dim[2];
   const int nbits = cells > 1 ? 32 - __clz(cells - 1) : 0;
+  const bool has_table = cells <= (uint32_t)cell_cap;   // bin-offset table below; else the search bisects
   if (tid == 0) {
     float* m = cloud_meta + 8 * b;
     m[0] = vminx; m[1] = vminy; m[2] = vminz; m[3] = voxel;
     m[4] = __int_as_float(dim[0]); m[5] = __int_as_float(dim[1]); m[6] = __int_as_float(dim[2]);
-    m[7] = __int_as_float(nbits);
+    m[7] = __int_as_float(nbits | (has_table ? 256 : 0));
   }
 
   // ---- voxel keys ---------------------------------------------------------------------------------
@@ -98,6 +99,42 @@ k_cloud_sort(const float* __restrict__ points, int N, float voxel, float* __rest
   RadixTables tb{base, wsum, wcount, wpre};
   radix_sort_pairs(kin, iin, kout, iout, N, 0, nbits, tb);
 
+  // ---- bin offsets: start[c] = first sorted position whose key is >= c, for c in [0, cells] ---------------
+  // (the reference's cell_start scan, tf_conv3p_atrous.cpp:203-214, as a lower-bound table: a run of grid cells
+  // [c0, c1] of one grid row is the contiguous range [start[c0], start[c1 + 1]) of the sorted cloud)
+  if (has_table) {
+    uint32_t* start = cell_start + (size_t)b * ((size_t)cell_cap + 1);
+    for (uint32_t c = tid; c <= cells; c += SORT_THREADS) start[c] = (uint32_t)N;
+    __syncthreads();
+    for (int s = tid; s < N; s += SORT_THREADS) {
+      const uint32_t k = kin[s];
+      if (s == 0 || kin[s - 1] != k) start[k] = (uint32_t)s;   // first position of every occupied cell
+    }
+    __syncthreads();
+    // empty cells take the start of the next occupied one: a suffix minimum (occupied starts increase with c)
+    const uint32_t per = (cells + 1 + SORT_THREADS - 1) / SORT_THREADS;
+    const uint32_t c_lo = min((uint32_t)tid * per, cells + 1), c_hi = min(c_lo + per, cells + 1);
+    uint32_t m = (uint32_t)N;
+    for (uint32_t c = c_hi; c > c_lo; --c) m = min(m, start[c - 1]);
+    // suffix minimum over the threads' chunk minima (reuses the digit table of the sort)
+    uint32_t v = m;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_down_sync(C3P_FULL_MASK, v, o);
+      if (lane + o < 32) v = min(v, u);
+    }
+    if (lane == 0) base[warp] = v;          // minimum of the warp's chunks
+    __syncthreads();
+    uint32_t later = (uint32_t)N;           // minimum over all chunks after this thread's
+    for (int w = warp + 1; w < SORT_WARPS; ++w) later = min(later, base[w]);
+    const uint32_t nxt = __shfl_down_sync(C3P_FULL_MASK, v, 1);   // suffix minimum starting at the next lane
+    if (lane < 31) later = min(later, nxt);
+    uint32_t run = later;
+    for (uint32_t c = c_hi; c > c_lo; --c) {
+      run = min(run, start[c - 1]);
+      start[c - 1] = run;
+    }
+  }
+
   // ---- emit sorted keys and (x, y, z, index) ------------------------------------------------------
   for (int s = tid; s < N; s += SORT_THREADS) {
     uint32_t idx = iin[s];
@@ -113,7 +150,7 @@ int launch_cloud_sort(const conv3p_geom_t* g, const float* points, const PlanVie
   {
     LaunchTimer timer_("k_cloud_sort", stream);
     k_cloud_sort<<<g->B, SORT_THREADS, 0, stream>>>(points, g->N, g->voxel_size, v.cloud_meta,
-                                                 v.sorted_key, v.sorted_xyzi, v.sort_tmp);
+                                                 v.sorted_key, v.sorted_xyzi, v.sort_tmp, v.cell_start, v.cell_cap);
   }
   C3P_LAUNCH_CHECK("k_cloud_sort");
   return CONV3P_OK;
