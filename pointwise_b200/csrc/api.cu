@@ -492,12 +492,23 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
     const size_t base = conv3p_scratch_bytes(geom, Cin, Cout);
     if (gsb && scratch && scratch_bytes >= base + gsb) g_store = reinterpret_cast<float*>(static_cast<char*>(scratch) + base);
   }
+  // scratch layout: [weight panel images | 128-row work-item lists | grad_filter scratch (its 64-row lists first)]
+  const size_t wpb = weight_panel_bytes(Cin, Cout) + tc_items_bytes(geom, Cin, Cout);
+  // Both gradients on tensor cores with 64-point tiles in the weight gradient: the pre-pass of the grad_input
+  // kernel also emits the weight-gradient kernel's lists (one walk over the count table instead of two).
+  bool items_shared = false;
+  GroupItems gi64{};
+  if (gi_tc && gf_tc && backward_filter2_tile_rows(geom->N, geom->pair_capacity, Cin, Cout) == 64 && scratch &&
+      scratch_bytes >= wpb + backward_filter2_scratch_bytes(geom, Cin, Cout)) {
+    gi64 = carve_group_items(static_cast<char*>(scratch) + wpb, (long long)geom->B * geom->N, 64);
+    items_shared = true;
+  }
   if (grad_input) {
     if (!filter) return CONV3P_ERR_INVALID_ARGUMENT;
     if (gi_tc) {
       if (!scratch || scratch_bytes < weight_panel_bytes(Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
       st = launch_backward_input_tc(geom, v, grad_output, filter, Cin, Cout, grad_input, scratch,
-                                    scratch_bytes, stream, g_store);
+                                    scratch_bytes, stream, g_store, items_shared ? &gi64 : nullptr);
     } else if (engine_allows_small() && small_backward_input_supported(Cin, Cout)) {
       st = launch_backward_input_small(geom, v, grad_output, filter, Cin, Cout, grad_input, stream);
     } else {
@@ -507,11 +518,10 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
   }
   if (grad_filter) {
     if (!input) return CONV3P_ERR_INVALID_ARGUMENT;
-    const size_t wpb = weight_panel_bytes(Cin, Cout) + tc_items_bytes(geom, Cin, Cout);
     if (!scratch || scratch_bytes < wpb) return CONV3P_ERR_BUFFER_TOO_SMALL;
     if (gf_tc)
       st = launch_backward_filter2(geom, v, grad_output, input, Cin, Cout, grad_filter,
-                                   static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream, g_store);
+                                   static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream, g_store, items_shared);
     else if (engine_allows_small() && small_backward_filter_supported(Cin, Cout))
       st = launch_backward_filter_small(geom, v, grad_output, input, Cin, Cout, grad_filter,
                                         static_cast<char*>(scratch) + wpb, scratch_bytes - wpb, stream);

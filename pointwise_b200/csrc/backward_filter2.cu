@@ -587,6 +587,11 @@ bool backward_filter2_supported(int N, long long capacity, int Cin, int Cout) {
   return w2_config(N, capacity, Cin, Cout, &c);
 }
 
+int backward_filter2_tile_rows(int N, long long capacity, int Cin, int Cout) {
+  W2Config c;
+  return w2_config(N, capacity, Cin, Cout, &c) ? c.PTS : 0;
+}
+
 static int w2_grid(long long tiles) {
   const int sms = sm_count();
   return (int)(tiles < sms ? (tiles < 1 ? 1 : tiles) : sms);
@@ -629,7 +634,7 @@ static int w2_dispatch(const W2Config& c, const W2Args& a, int grid, cudaStream_
 
 int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const float* grad_out, const float* input,
                             int Cin, int Cout, float* grad_filter, void* scratch, size_t scratch_bytes,
-                            cudaStream_t stream, const float* g_store) {
+                            cudaStream_t stream, const float* g_store, bool items_ready) {
   const long long nW = (long long)C3P_NCELL * Cin * Cout;
   const long long pts = (long long)g->B * g->N;
   if (pts == 0) {
@@ -641,7 +646,7 @@ int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const flo
   if (!scratch || scratch_bytes < backward_filter2_scratch_bytes(g, Cin, Cout)) return CONV3P_ERR_BUFFER_TOO_SMALL;
   const GroupItems gi = carve_group_items(scratch, pts, c.PTS);
   float* partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + group_items_bytes(pts, c.PTS));
-  int st = launch_group_items(g, v, true, c.PTS, gi, stream);
+  int st = items_ready ? CONV3P_OK : launch_group_items(g, v, true, c.PTS, gi, stream);   // (else built with grad_input's)
   if (st) return st;
   const int grid = w2_grid(gi.subtiles);
   if (grid > 256) return CONV3P_ERR_UNSUPPORTED;

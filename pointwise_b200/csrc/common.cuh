@@ -102,12 +102,15 @@ int launch_backward_filter_simt(const conv3p_geom_t* g, const PlanView& v, const
                                 void* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t backward_filter_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout);
 
+struct GroupItems;   // work-item lists of the tensor-core kernels (below)
+
 // tensor-core (tcgen05, 3xTF32) engine
 bool forward_tc_supported(int N, long long capacity, int Cin, int Cout);
 bool backward_input_tc_supported(int N, long long capacity, int Cin, int Cout);
 int launch_backward_input_tc(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
                              const float* filter, int Cin, int Cout, float* grad_input, void* scratch,
-                             size_t scratch_bytes, cudaStream_t stream, float* g_store = nullptr);
+                             size_t scratch_bytes, cudaStream_t stream, float* g_store = nullptr,
+                             const GroupItems* half_items = nullptr);
 size_t weight_panel_bytes(int Cin, int Cout);
 int launch_prep_weight_panels(const float* filter, void* wp, int Cin, int Cout, int transposed_out,
                               cudaStream_t stream);
@@ -130,11 +133,13 @@ struct GroupItems {
 };
 size_t group_items_bytes(long long pts, int rows);
 GroupItems carve_group_items(void* scratch, long long pts, int rows);
+// `half` (rows == 128 only): also emit the lists of the 64-row tiles (two per sub-tile) into *half
 int launch_group_items(const conv3p_geom_t* g, const PlanView& v, bool backward_lists, int rows,
-                       const GroupItems& gi, cudaStream_t stream);
+                       const GroupItems& gi, cudaStream_t stream, const GroupItems* half = nullptr);
 int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* src, const void* wp, int Csrc,
                        int Nout, float* out, bool weighted, void* scratch, size_t scratch_bytes, const char* name,
-                       cudaStream_t stream, float* g_store = nullptr, const RowIO& io = RowIO());
+                       cudaStream_t stream, float* g_store = nullptr, const RowIO& io = RowIO(),
+                       const GroupItems* half_items = nullptr);
 // scratch layout of one forward / backward call: [weight panel images | work-item lists | grad_filter partials]
 size_t tc_items_bytes(const conv3p_geom_t* g, int Cin, int Cout);
 
@@ -143,7 +148,8 @@ bool backward_filter2_supported(int N, long long capacity, int Cin, int Cout);
 size_t backward_filter2_scratch_bytes(const conv3p_geom_t* g, int Cin, int Cout);
 int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const float* grad_out, const float* input,
                             int Cin, int Cout, float* grad_filter, void* scratch, size_t scratch_bytes,
-                            cudaStream_t stream, const float* g_store = nullptr);
+                            cudaStream_t stream, const float* g_store = nullptr, bool items_ready = false);
+int backward_filter2_tile_rows(int N, long long capacity, int Cin, int Cout);   // 64 or 32 (0: shape not supported)
 
 // warp-per-point fp32 engine for the reference models' small channel counts (3, 9, 13, 36)
 bool small_channels_supported(int Cin, int Cout);

@@ -79,12 +79,22 @@ __device__ unsigned long long g2_cta_cycles[2];
 // population class (0: more than 8 members, 1: 5..8, 2: 1..4, 3: empty): warp ballots give the rank inside the
 // warp, per-warp class counts (one byte each) go through shared memory, so item index = class base + rank.
 // The 27 lists of the sub-tile are staged in shared memory and written out with coalesced 16-byte stores.
-template <int ROWS>
+// HALF (ROWS == 128 only): the same pass also emits the lists of the two 64-row tiles of the sub-tile (the weight-gradient
+// kernel's tiling) -- the count table is read once for both gradient kernels instead of once per kernel.
+struct HalfLists {
+  uint2* items;      // [2 * subtiles][27][64]
+  int* nnz;          // [2 * subtiles][27]
+  int* rowid;        // [2 * subtiles * 64]
+  unsigned* mask;    // [2 * subtiles]
+  long long tiles;   // number of 64-row tiles (the second half of the last sub-tile may not exist)
+};
+
+template <int ROWS, bool HALF>
 __global__ void __launch_bounds__(ROWS)
 k_group_items(const int* __restrict__ cnt, const long long* __restrict__ begin, const int* __restrict__ len,
               const float4* __restrict__ sorted_xyzi, long long total_points, long long capacity, int N,
               uint2* __restrict__ g_items, int* __restrict__ g_nnz, int* __restrict__ g_rowid,
-              unsigned* __restrict__ g_mask, unsigned* __restrict__ g_counter) {
+              unsigned* __restrict__ g_mask, unsigned* __restrict__ g_counter, HalfLists half) {
   constexpr int NW = ROWS / 32;
   __shared__ uint2 stage[C3P_NCELL * ROWS];
   __shared__ uint32_t wcls[C3P_NCELL][NW];  // per warp: rows of class 0..3, one byte each
@@ -151,6 +161,47 @@ k_group_items(const int* __restrict__ cnt, const long long* __restrict__ begin, 
   const uint4* src = reinterpret_cast<const uint4*>(stage);
   uint4* dst = reinterpret_cast<uint4*>(g_items + sub * C3P_NCELL * ROWS);
   for (int e = r; e < C3P_NCELL * ROWS / 2; e += ROWS) dst[e] = src[e];
+  if (HALF) {
+    // the two 64-row tiles: rank among the tile's two warps; stage[f][tile][idx] has the layout of two consecutive tiles
+    static_assert(!HALF || ROWS == 128, "half lists are the two 64-row tiles of a 128-row sub-tile");
+    __syncthreads();
+    const int tile = warp >> 1, r64 = r & 63;
+    const bool tile_ok = sub * 2 + tile < half.tiles;
+    if (tile_ok) half.rowid[s] = row;
+    uint32_t p2 = 0;
+    {   // list position of the row's first entry (recomputed: pos was advanced past the last cell above)
+      int tot = 0;
+#pragma unroll
+      for (int f = 0; f < C3P_NCELL; ++f) tot += c[f];
+      p2 = pos - (uint32_t)tot;
+    }
+    unsigned hmask = 0;
+#pragma unroll
+    for (int f = 0; f < C3P_NCELL; ++f) {
+      const int cls = (int)(rank[f] & 255u);
+      int idx = (int)(rank[f] >> 8), nonempty = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < 2; ++w2) {
+        const int w = tile * 2 + w2;
+        const uint32_t pk = wcls[f][w];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int v = (int)((pk >> (8 * k)) & 255u);
+          if (k < cls || (k == cls && w < warp)) idx += v;
+          if (k < 3) nonempty += v;
+        }
+      }
+      stage[(tile * C3P_NCELL + f) * 64 + idx] = make_uint2(p2, (uint32_t)r64 | ((uint32_t)c[f] << 8));
+      p2 += (uint32_t)c[f];
+      if (nonempty) hmask |= 1u << f;
+      if (r64 == f && tile_ok) half.nnz[(sub * 2 + tile) * C3P_NCELL + f] = nonempty;
+    }
+    if (r64 == 0 && tile_ok) half.mask[sub * 2 + tile] = hmask;
+    __syncthreads();
+    uint4* dst2 = reinterpret_cast<uint4*>(half.items + sub * 2 * C3P_NCELL * 64);
+    const int n16 = (sub * 2 + 1 < half.tiles ? 2 : 1) * C3P_NCELL * 64 / 2;   // 16-byte units of the existing tiles
+    for (int e = r; e < n16; e += ROWS) dst2[e] = src[e];
+  }
 }
 
 // Barrier slots of k_gather_mma2 in one shared array, addressed as bars + 8 * index.
@@ -635,24 +686,22 @@ GroupItems carve_group_items(void* scratch, long long pts, int rows) {
 }
 
 int launch_group_items(const conv3p_geom_t* g, const PlanView& v, bool backward_lists, int rows,
-                       const GroupItems& gi, cudaStream_t stream) {
+                       const GroupItems& gi, cudaStream_t stream, const GroupItems* half) {
   const long long pts = (long long)g->B * g->N;
   if (pts == 0) return CONV3P_OK;
   const int* cnt = backward_lists ? v.bwd_count : v.count_table;
+  HalfLists h{};
+  if (half) { h.items = half->items; h.nnz = half->nnz; h.rowid = half->rowid; h.mask = half->mask; h.tiles = half->subtiles; }
+  if (half && rows != 128) return CONV3P_ERR_INVALID_ARGUMENT;
   {
     LaunchTimer timer_("k_group_items", stream);
-    if (rows == 128)
-      k_group_items<128><<<(unsigned)gi.subtiles, 128, 0, stream>>>(cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts,
-                                                                    g->pair_capacity, g->N, gi.items, gi.nnz,
-                                                                    gi.rowid, gi.mask, gi.counter);
-    else if (rows == 64)
-      k_group_items<64><<<(unsigned)gi.subtiles, 64, 0, stream>>>(cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts,
-                                                                  g->pair_capacity, g->N, gi.items, gi.nnz, gi.rowid,
-                                                                  gi.mask, gi.counter);
-    else
-      k_group_items<32><<<(unsigned)gi.subtiles, 32, 0, stream>>>(cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts,
-                                                                  g->pair_capacity, g->N, gi.items, gi.nnz, gi.rowid,
-                                                                  gi.mask, gi.counter);
+#define C3P_GI_ARGS cnt, v.pair_begin, v.pair_len, v.sorted_xyzi, pts, g->pair_capacity, g->N, gi.items, gi.nnz, gi.rowid, \
+                    gi.mask, gi.counter, h
+    if (rows == 128 && half) k_group_items<128, true><<<(unsigned)gi.subtiles, 128, 0, stream>>>(C3P_GI_ARGS);
+    else if (rows == 128) k_group_items<128, false><<<(unsigned)gi.subtiles, 128, 0, stream>>>(C3P_GI_ARGS);
+    else if (rows == 64) k_group_items<64, false><<<(unsigned)gi.subtiles, 64, 0, stream>>>(C3P_GI_ARGS);
+    else k_group_items<32, false><<<(unsigned)gi.subtiles, 32, 0, stream>>>(C3P_GI_ARGS);
+#undef C3P_GI_ARGS
   }
   C3P_LAUNCH_CHECK("k_group_items");
   return CONV3P_OK;
@@ -662,7 +711,7 @@ size_t gather_mma2_scratch_bytes(const conv3p_geom_t* g) { return group_items_by
 
 int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* src, const void* wp, int Csrc,
                        int Nout, float* out, bool weighted, void* scratch, size_t scratch_bytes, const char* name,
-                       cudaStream_t stream, float* g_store, const RowIO& io) {
+                       cudaStream_t stream, float* g_store, const RowIO& io, const GroupItems* half_items) {
   G2Config c;
   const long long pts = (long long)g->B * g->N;
   if (!g2_config(g->N, g->pair_capacity, Csrc, Nout, &c)) return CONV3P_ERR_UNSUPPORTED;
@@ -671,7 +720,7 @@ int launch_gather_mma2(const conv3p_geom_t* g, const PlanView& v, const float* s
   const GroupItems gi = carve_group_items(scratch, pts, 128);
   const long long subtiles = gi.subtiles;
   {
-    const int st = launch_group_items(g, v, weighted, 128, gi, stream);
+    const int st = launch_group_items(g, v, weighted, 128, gi, stream, half_items);
     if (st) return st;
   }
   G2Args a{};

@@ -96,14 +96,14 @@ int launch_forward_tc(const conv3p_geom_t* g, const PlanView& v, const float* in
 
 int launch_backward_input_tc(const conv3p_geom_t* g, const PlanView& v, const float* grad_out,
                              const float* filter, int Cin, int Cout, float* grad_input, void* scratch,
-                             size_t scratch_bytes, cudaStream_t stream, float* g_store) {
+                             size_t scratch_bytes, cudaStream_t stream, float* g_store, const GroupItems* half_items) {
   if (!backward_input_tc_supported(g->N, g->pair_capacity, Cin, Cout)) return CONV3P_ERR_UNSUPPORTED;
   const size_t wpb = weight_panel_bytes(Cin, Cout);
   if (!scratch || scratch_bytes < wpb) return CONV3P_ERR_BUFFER_TOO_SMALL;
   int st = launch_prep_weight_panels(filter, scratch, Cin, Cout, 1, stream);
   if (st) return st;
   return launch_gather_mma2(g, v, grad_out, scratch, Cout, Cin, grad_input, true, static_cast<char*>(scratch) + wpb,
-                            scratch_bytes - wpb, "k_backward_input_tc", stream, g_store);
+                            scratch_bytes - wpb, "k_backward_input_tc", stream, g_store, RowIO(), half_items);
 }
 
 }  // namespace c3p
