@@ -18,7 +18,9 @@
  *   filter  [3,3,3,Cin,Cout] float32, dims ordered z,y,x; weight index (f*Cin+k)*Cout+c,
  *           f = (fz*3+fy)*3+fx                    output  [B,N,Cout] float32
  *   stride  int[3] in x,y,z order                 voxel_size  float
- * Only 3x3x3 filters (every reference model) and float32 are supported.
+ * float32 only.  3x3x3 filters (every reference model) run on the tuned engines through the plan calls below; other
+ * filter shapes (the reference reads fz, fy, fx from the tensor, tf_conv3p_atrous.cpp:425-427) are served by the
+ * one-shot conv3p_op_* calls on a general fp32 path (up to 512 cells).
  *
  * Memory: the library never allocates device memory.  The caller owns inputs, outputs, the plan
  * buffer and the scratch buffer (sizes from the *_bytes functions).  Outputs are fully overwritten.
@@ -43,7 +45,7 @@ enum {
   CONV3P_ERR_INVALID_ARGUMENT = 1, /* shapes / strides / voxel size rejected */
   CONV3P_ERR_BUFFER_TOO_SMALL = 2, /* plan or scratch buffer smaller than *_bytes() */
   CONV3P_ERR_CUDA = 3,             /* a CUDA runtime call failed; see conv3p_last_cuda_error */
-  CONV3P_ERR_UNSUPPORTED = 4,      /* e.g. filter not 3x3x3 */
+  CONV3P_ERR_UNSUPPORTED = 4,      /* e.g. a filter with more than 512 cells */
   CONV3P_ERR_PAIR_OVERFLOW = 5,    /* reported by conv3p_plan_stats: pair_capacity too small */
   CONV3P_ERR_NO_BACKWARD_LISTS = 6 /* conv3p_backward_f32 on a plan that conv3p_plan_build_f32 built in this process
                                       and conv3p_plan_build_backward has not completed (tracked per plan address) */
@@ -180,6 +182,11 @@ size_t conv3p_op_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout);
 /* >= conv3p_op_workspace_bytes: with this much workspace conv3p_op_backward_f32 (and conv3p_host_backward_f32 for
  * its device part) shares one gather between the two gradients, see conv3p_backward_scratch_bytes. */
 size_t conv3p_op_backward_workspace_bytes(const conv3p_geom_t* geom, int Cin, int Cout);
+
+/* Workspace of a one-shot call for ANY supported filter shape (filter_dims = {fz,fy,fx}); backward != 0 sizes it for
+ * conv3p_op_backward_f32 (3x3x3: with the shared gather).  0 = unsupported shape / invalid geometry. */
+size_t conv3p_op_workspace_bytes_ex(const conv3p_geom_t* geom, const int filter_dims[3], int Cin, int Cout,
+                                    int backward);
 
 int conv3p_op_forward_f32(const float* points, const float* input, const float* filter,
                           const int filter_dims[3], const int stride_xyz[3], float voxel_size, int B,

@@ -208,11 +208,13 @@ class Ref:
             raise ValueError(self._err())
         return gi, gf
 
-    def neighbor_count(self, xyz, stride, voxel):
+    def neighbor_count(self, xyz, stride, voxel, dims=(3, 3, 3)):
+        """dims = (fz, fy, fx): the reference is generic in the filter shape (tf_conv3p_atrous.cpp:425-427)."""
         xyz = _f32(xyz).reshape(-1, 3)
         n = xyz.shape[0]
-        out = np.zeros((n, NCELL), np.int32)
-        self.lib.ref_neighbor_count_f32(xyz, n, 3, 3, 3, _stride3(stride), float(np.float32(voxel)), out)
+        fz, fy, fx = (int(d) for d in dims)
+        out = np.zeros((n, fz * fy * fx), np.int32)
+        self.lib.ref_neighbor_count_f32(xyz, n, fz, fy, fx, _stride3(stride), float(np.float32(voxel)), out)
         return out
 
     def neighbors(self, xyz, stride, voxel):

@@ -263,7 +263,7 @@ const char* conv3p_status_string(int s) {
     case CONV3P_ERR_INVALID_ARGUMENT: return "invalid argument";
     case CONV3P_ERR_BUFFER_TOO_SMALL: return "plan/scratch/workspace buffer too small";
     case CONV3P_ERR_CUDA: return "CUDA runtime error";
-    case CONV3P_ERR_UNSUPPORTED: return "unsupported configuration (only 3x3x3 float32 filters)";
+    case CONV3P_ERR_UNSUPPORTED: return "unsupported configuration (filter with more than 512 cells)";
     case CONV3P_ERR_PAIR_OVERFLOW: return "pair_capacity too small for this batch";
     case CONV3P_ERR_NO_BACKWARD_LISTS: return "backward lists not built";
     default: return "unknown status";
@@ -547,10 +547,21 @@ size_t conv3p_op_backward_workspace_bytes(const conv3p_geom_t* geom, int Cin, in
   return p + conv3p_backward_scratch_bytes(geom, Cin, Cout);
 }
 
+// 3x3x3 (every reference model) runs on the tuned engines; other shapes on the general path (generic_filter.cu)
+static bool is_333(const int d[3]) { return d[0] == 3 && d[1] == 3 && d[2] == 3; }
 static int check_filter_dims(const int filter_dims[3]) {
   if (!filter_dims) return CONV3P_ERR_INVALID_ARGUMENT;
-  if (filter_dims[0] != 3 || filter_dims[1] != 3 || filter_dims[2] != 3) return CONV3P_ERR_UNSUPPORTED;
+  if (filter_dims[0] < 1 || filter_dims[1] < 1 || filter_dims[2] < 1) return CONV3P_ERR_INVALID_ARGUMENT;
+  if (!is_333(filter_dims) && !generic_filter_supported(filter_dims)) return CONV3P_ERR_UNSUPPORTED;
   return CONV3P_OK;
+}
+
+size_t conv3p_op_workspace_bytes_ex(const conv3p_geom_t* geom, const int filter_dims[3], int Cin, int Cout,
+                                    int backward) {
+  if (!filter_dims || check_filter_dims(filter_dims)) return 0;
+  if (is_333(filter_dims))
+    return backward ? conv3p_op_backward_workspace_bytes(geom, Cin, Cout) : conv3p_op_workspace_bytes(geom, Cin, Cout);
+  return generic_workspace_bytes(geom, filter_dims, Cin, Cout);
 }
 
 int conv3p_op_forward_f32(const float* points, const float* input, const float* filter,
@@ -563,6 +574,11 @@ int conv3p_op_forward_f32(const float* points, const float* input, const float* 
   conv3p_geom_t g = make_geom(B, N, stride_xyz, voxel_size, pair_capacity);
   st = check_geom(&g);
   if (st) return st;
+  if (!is_333(filter_dims)) {
+    st = check_channels(Cin, Cout);
+    if (st) return st;
+    return generic_forward(&g, filter_dims, points, input, filter, Cin, Cout, output, workspace, workspace_bytes, stream);
+  }
   const size_t pb = conv3p_plan_bytes(&g);
   if (!workspace || workspace_bytes < conv3p_op_workspace_bytes(&g, Cin, Cout))
     return CONV3P_ERR_BUFFER_TOO_SMALL;
@@ -583,6 +599,12 @@ int conv3p_op_backward_f32(const float* grad_output, const float* points, const 
   conv3p_geom_t g = make_geom(B, N, stride_xyz, voxel_size, pair_capacity);
   st = check_geom(&g);
   if (st) return st;
+  if (!is_333(filter_dims)) {
+    st = check_channels(Cin, Cout);
+    if (st) return st;
+    return generic_backward(&g, filter_dims, grad_output, points, input, filter, Cin, Cout, grad_input, grad_filter,
+                            workspace, workspace_bytes, stream);
+  }
   const size_t pb = conv3p_plan_bytes(&g);
   if (!workspace || workspace_bytes < conv3p_op_workspace_bytes(&g, Cin, Cout))
     return CONV3P_ERR_BUFFER_TOO_SMALL;

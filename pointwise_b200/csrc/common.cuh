@@ -151,6 +151,16 @@ int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const flo
                             cudaStream_t stream, const float* g_store = nullptr, bool items_ready = false);
 int backward_filter2_tile_rows(int N, long long capacity, int Cin, int Cout);   // 64 or 32 (0: shape not supported)
 
+// general filter shapes (generic_filter.cu): any fz x fy x fx with at most 512 cells, fp32 SIMT, one-shot calls
+bool generic_filter_supported(const int dims_zyx[3]);
+size_t generic_workspace_bytes(const conv3p_geom_t* g, const int dims_zyx[3], int Cin, int Cout);
+int generic_forward(const conv3p_geom_t* g, const int dims_zyx[3], const float* points, const float* input,
+                    const float* filter, int Cin, int Cout, float* output, void* ws, size_t ws_bytes,
+                    cudaStream_t stream);
+int generic_backward(const conv3p_geom_t* g, const int dims_zyx[3], const float* grad_out, const float* points,
+                     const float* input, const float* filter, int Cin, int Cout, float* grad_input,
+                     float* grad_filter, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 // warp-per-point fp32 engine for the reference models' small channel counts (3, 9, 13, 36)
 bool small_channels_supported(int Cin, int Cout);
 bool small_forward_supported(int Cin, int Cout);         // per direction (36->13 forward yes, 13->36 grad_input no)

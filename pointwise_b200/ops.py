@@ -91,8 +91,8 @@ def validate(points, input, kernel):
         raise ValueError("Conv3p expects a [fz, fy, fx, in_channels, out_channels] filter")
     if kernel.shape[3] != input.shape[2]:
         raise ValueError("Conv3p expects filter channels to be matched with input channels")  # :430
-    if tuple(kernel.shape[:3]) != (3, 3, 3):
-        raise NotImplementedError("conv3p_b200 supports 3x3x3 filters only (all reference models)")
+    if any(int(d) < 1 for d in kernel.shape[:3]):
+        raise ValueError("Conv3p expects a [fz, fy, fx, in_channels, out_channels] filter")
 
 
 def _stream_ptr(device) -> C.c_void_p:
@@ -558,11 +558,77 @@ class _Conv3pFunction(torch.autograd.Function):
         return None, gi, gf, None, None
 
 
+# --------------------------------------------------------------------------------------------------
+# general filter shapes (anything but 3x3x3): one-shot calls of the general fp32 path
+# --------------------------------------------------------------------------------------------------
+_generic_capacity_hint: dict = {}
+
+
+def _generic_call(points, stride, voxel, dims, Cin, Cout, backward, run):
+    """Runs a one-shot C entry point on a workspace sized for `capacity` pairs; grows the capacity and retries when
+    the neighbour lists overflowed (one 128-byte read-back per call: this path is the reference-compatible fallback
+    for filter shapes no model uses, not the tuned one)."""
+    L = _lib.lib()
+    B, N = int(points.shape[0]), int(points.shape[1])
+    key = (B, N, stride, voxel, dims)
+    vol = dims[0] * dims[1] * dims[2]
+    cap = _generic_capacity_hint.get(key, max(1024, 2 * vol * B * N))
+    dims_c = (C.c_int * 3)(*dims)
+    stride_c = (C.c_int * 3)(*stride)
+    while True:
+        geom = _lib.make_geom(B, N, stride, voxel, cap)
+        nbytes = L.conv3p_op_workspace_bytes_ex(geom, dims_c, Cin, Cout, 1 if backward else 0)
+        if nbytes == 0:
+            raise _lib.Conv3pError(_lib.ERR_UNSUPPORTED, f"filter shape {dims} is not supported (more than 512 cells)")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device)
+        with torch.cuda.device(points.device):
+            _lib.check(run(L, dims_c, stride_c, cap, ws, nbytes))
+            st = _lib.PlanStats()
+            _lib.check(L.conv3p_plan_stats(geom, _ptr(ws), st, _stream_ptr(points.device)))
+        if not st.overflow:
+            _generic_capacity_hint[key] = max(_generic_capacity_hint.get(key, 0), int(st.total_pairs * 1.25) + 1024)
+            return
+        cap = int(st.total_pairs * 1.125) + 1024
+
+
+class _Conv3pGenericFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, input, kernel, stride, voxel):
+        dims = tuple(int(d) for d in kernel.shape[:3])
+        Cin, Cout = int(kernel.shape[3]), int(kernel.shape[4])
+        B, N = int(points.shape[0]), int(points.shape[1])
+        out = torch.empty((B, N, Cout), dtype=torch.float32, device=points.device)
+        _generic_call(points, stride, voxel, dims, Cin, Cout, False,
+                      lambda L, d, s, cap, ws, nb: L.conv3p_op_forward_f32(
+                          _ptr(points), _ptr(input), _ptr(kernel), d, s, voxel, B, N, Cin, Cout, cap, _ptr(out),
+                          _ptr(ws), nb, _stream_ptr(points.device)))
+        ctx.save_for_backward(points, input, kernel)
+        ctx.geometry = (stride, voxel)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        points, input, kernel = ctx.saved_tensors
+        stride, voxel = ctx.geometry
+        grad_output = _check_cuda_f32(grad_output, "grad_output")
+        dims = tuple(int(d) for d in kernel.shape[:3])
+        Cin, Cout = int(kernel.shape[3]), int(kernel.shape[4])
+        B, N = int(points.shape[0]), int(points.shape[1])
+        gi = torch.empty_like(input)
+        gf = torch.empty_like(kernel)
+        _generic_call(points, stride, voxel, dims, Cin, Cout, True,
+                      lambda L, d, s, cap, ws, nb: L.conv3p_op_backward_f32(
+                          _ptr(grad_output), _ptr(points), _ptr(input), _ptr(kernel), d, s, voxel, B, N, Cin, Cout, cap,
+                          _ptr(gi), _ptr(gf), _ptr(ws), nb, _stream_ptr(points.device)))
+        return None, gi, gf, None, None
+
+
 def conv3p(points_tensor, input_tensor, kernel_tensor, stride, voxel_size,
            plan: Optional[NeighborPlan] = None, activation: Optional[str] = None) -> torch.Tensor:
     """Drop-in for the reference's ``conv3p`` (pointcnn2_acsd.py:12-13): same positional signature.
 
-    points [B,N,3], input [B,N,Cin], kernel [3,3,3,Cin,Cout] (z,y,x,in,out), stride = 3 ints (x,y,z),
+    points [B,N,3], input [B,N,Cin], kernel [fz,fy,fx,Cin,Cout] (z,y,x,in,out; 3x3x3 in every reference model and on
+    the tuned engines, any shape up to 512 cells on the general path), stride = 3 ints (x,y,z),
     voxel_size = 1 float; returns [B,N,Cout].  Differentiable w.r.t. input and kernel only
     (pointcnn2_acsd.py:31).  ``plan`` optionally reuses a NeighborPlan built for the same points,
     stride and voxel size (e.g. across layers).  ``activation="selu"`` returns ``selu(conv3p(...))`` with the
@@ -573,12 +639,17 @@ def conv3p(points_tensor, input_tensor, kernel_tensor, stride, voxel_size,
     kernel = _check_cuda_f32(kernel_tensor, "kernel")
     validate(points, input, kernel)
     s, v = parse_stride(stride), parse_voxel(voxel_size)
+    if activation not in ACTIVATIONS:
+        raise ValueError(f"Conv3p: unknown activation {activation!r}")
+    if tuple(kernel.shape[:3]) != (3, 3, 3):
+        # the reference is generic in the filter shape (tf_conv3p_atrous.cpp:425-427); anything but 3x3x3 takes the
+        # general fp32 path (no plan reuse, no fused epilogue)
+        y = _Conv3pGenericFunction.apply(points, input, kernel, s, v)
+        return torch.nn.functional.selu(y) if activation == "selu" else y
     if plan is None:
         plan = NeighborPlan(points, s, v)
     elif not plan.matches(points, s, v):
         raise ValueError("Conv3p: the supplied NeighborPlan was built for different points/stride/voxel_size")
-    if activation not in ACTIVATIONS:
-        raise ValueError(f"Conv3p: unknown activation {activation!r}")
     return _Conv3pFunction.apply(points, input, kernel, plan, None if activation in (None, "none") else activation)
 
 
@@ -591,6 +662,14 @@ def conv3p_grad(grad_from_next, points, input, filter, stride, voxel_size,
     filter = _check_cuda_f32(filter, "filter")
     validate(points, input, filter)
     s, v = parse_stride(stride), parse_voxel(voxel_size)
+    if tuple(filter.shape[:3]) != (3, 3, 3):
+        class _Ctx:      # the autograd node's backward, called directly
+            pass
+        ctx = _Ctx()
+        ctx.saved_tensors = (points, input, filter)
+        ctx.geometry = (s, v)
+        _, gi, gf, _, _ = _Conv3pGenericFunction.backward(ctx, grad_from_next)
+        return gi, gf
     if plan is None:
         plan = NeighborPlan(points, s, v)
     return conv3p_backward(plan, grad_from_next, input, filter)

@@ -36,10 +36,21 @@ RANDOM = {  # name: (B, N, Cin, Cout, stride, dist, quantise, seed)
 }
 
 
+# Filter shapes other than 3x3x3 (the reference reads fz, fy, fx from the tensor, tf_conv3p_atrous.cpp:425-427):
+# name: (B, N, Cin, Cout, (fz, fy, fx), stride, dist, quantise, seed)
+GENERAL = {
+    "gen_555_s1": (2, 300, 3, 4, (5, 5, 5), (1, 1, 1), "room", None, 21),
+    "gen_135_s2": (1, 400, 2, 3, (1, 3, 5), (2, 2, 2), "sphere", None, 22),
+    "gen_222_q": (2, 256, 4, 2, (2, 2, 2), (1, 1, 1), "cube", 0.05, 23),
+    "gen_331_aniso": (1, 350, 3, 3, (3, 3, 1), (1, 2, 3), "room", 0.05, 24),
+    "gen_111": (1, 128, 5, 6, (1, 1, 1), (1, 1, 1), "cube", None, 25),
+}
+
+
 def run(R, points, inp, filt, gout, stride):
     out = R.forward(points, inp, filt, stride, V)
     gi, gf = R.backward(gout, points, inp, filt, stride, V)
-    cnt = np.stack([R.neighbor_count(points[b], stride, V) for b in range(points.shape[0])])
+    cnt = np.stack([R.neighbor_count(points[b], stride, V, dims=filt.shape[:3]) for b in range(points.shape[0])])
     return dict(points=points, input=inp, filter=filt, grad_out=gout,
                 stride=np.asarray(np.broadcast_to(stride, (3,)), np.int32), voxel=np.float32(V),
                 output=out, grad_input=gi, grad_filter=gf, count_table=cnt)
@@ -57,7 +68,12 @@ def main():
         pr = make_problem(B, N, Ci, Co, dist, seed=seed, quantise=q)
         np.savez_compressed(os.path.join(HERE, name + ".npz"),
                             **run(R, pr["points"], pr["input"], pr["filter"], pr["grad_out"], s))
-    print("wrote", len(KATS) + len(RANDOM), "fixtures to", HERE)
+    for name, (B, N, Ci, Co, dims, s, dist, q, seed) in GENERAL.items():
+        pr = make_problem(B, N, Ci, Co, dist, seed=seed, quantise=q)
+        filt = np.random.default_rng(seed).uniform(-0.1, 0.1, (*dims, Ci, Co)).astype(np.float32)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"),
+                            **run(R, pr["points"], pr["input"], filt, pr["grad_out"], s))
+    print("wrote", len(KATS) + len(RANDOM) + len(GENERAL), "fixtures to", HERE)
 
 
 if __name__ == "__main__":

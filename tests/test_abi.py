@@ -73,9 +73,15 @@ def test_buffer_checks_precede_any_cuda_call(L):
     g = _lib.make_geom(2, 8, (1, 1, 1), 0.1, 1000)
     assert L.conv3p_plan_build_f32(g, None, None, 0, None) == _lib.ERR_BUFFER_TOO_SMALL
     i3 = C.c_int * 3
+    st = L.conv3p_op_forward_f32(None, None, None, i3(9, 9, 9), i3(1, 1, 1), 0.1, 2, 8, 4, 4, 100, None,
+                                 None, 0, None)
+    assert st == _lib.ERR_UNSUPPORTED           # more than 512 cells
     st = L.conv3p_op_forward_f32(None, None, None, i3(3, 3, 5), i3(1, 1, 1), 0.1, 2, 8, 4, 4, 100, None,
                                  None, 0, None)
-    assert st == _lib.ERR_UNSUPPORTED
+    assert st == _lib.ERR_BUFFER_TOO_SMALL      # general filter path: workspace checked before any CUDA call
+    assert L.conv3p_op_workspace_bytes_ex(g, i3(3, 3, 5), 4, 4, 0) > L.conv3p_plan_bytes(g)
+    assert L.conv3p_op_workspace_bytes_ex(g, i3(3, 3, 3), 4, 4, 1) == L.conv3p_op_backward_workspace_bytes(g, 4, 4)
+    assert L.conv3p_op_workspace_bytes_ex(g, i3(9, 9, 9), 4, 4, 0) == 0
     st = L.conv3p_op_forward_f32(None, None, None, i3(3, 3, 3), i3(1, 1, 1), 0.1, 2, 8, 4, 4, 100, None,
                                  None, 0, None)
     assert st == _lib.ERR_BUFFER_TOO_SMALL

@@ -369,13 +369,13 @@ def test_c_abi_one_shot_and_host_calls(port):
     st = L.conv3p_host_forward_f32(p(pr["points"]), p(pr["input"]), p(pr["filter"]), i3(*stride), V, B,
                                    N, Cin, Cout, 100, p(out), C.c_void_p(ws.data_ptr()), ws.numel(), None)
     assert st == _lib.ERR_PAIR_OVERFLOW
-    # unsupported filter size -> status
+    # unsupported filter size (more than 512 cells) -> status
     P, X, W = dev(pr["points"]), dev(pr["input"]), dev(pr["filter"])
     Y = torch.empty(B, N, Cout, device="cuda")
     ws2 = torch.empty(L.conv3p_op_workspace_bytes(g, Cin, Cout), dtype=torch.uint8, device="cuda")
-    st = L.conv3p_op_forward_f32(P.data_ptr(), X.data_ptr(), W.data_ptr(), i3(5, 3, 3), i3(*stride), V, B,
+    st = L.conv3p_op_forward_f32(P.data_ptr(), X.data_ptr(), W.data_ptr(), i3(9, 9, 9), i3(*stride), V, B,
                                  N, Cin, Cout, cap, Y.data_ptr(), ws2.data_ptr(), ws2.numel(), None)
-    assert st == _lib.ERR_UNSUPPORTED
+    assert st == _lib.ERR_UNSUPPORTED          # more than 512 cells (other shapes: tests/test_gpu_generic.py)
     _lib.check(L.conv3p_op_forward_f32(P.data_ptr(), X.data_ptr(), W.data_ptr(), i3(3, 3, 3), i3(*stride),
                                        V, B, N, Cin, Cout, cap, Y.data_ptr(), ws2.data_ptr(),
                                        ws2.numel(), None))
