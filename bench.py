@@ -655,6 +655,13 @@ def gpu_arm(args):
                "efficiency_vs_own_n1": ms16_alone / ms16}
         del r16
 
+    refgpu = None
+    if world == 1 and args.workload == "headline" and not args.no_sweep:
+        try:
+            refgpu = reference_gpu_code(run)
+        except Exception as e:  # the baseline must never take the benchmark down
+            refgpu = {"value": None, "error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- BASELINE configs[3]: the 9-point sweep (one GPU) -----------------------------------------------------
     sweep = None
     if world == 1 and args.workload == "headline" and not args.no_sweep:
@@ -692,6 +699,8 @@ def gpu_arm(args):
         line["b16"] = b16
     if sweep:
         line["sweep"] = sweep
+    if refgpu:
+        line["reference_gpu_code"] = refgpu
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = run_cpu_baseline(args.workload)
     print(json.dumps(line), flush=True)
@@ -745,6 +754,42 @@ def run_sweep(L, device, warm=2, steps=5):
         del r
         torch.cuda.empty_cache()
     return out
+
+
+def reference_gpu_code(run: Runner, clouds=4, steps=3):
+    """The reference's own CUDA kernels (tf_conv3p_atrous.cu, compiled unmodified for sm_100a with its own flags:
+    oracle/_ref/libconv3p_ref_gpu.so) on a bounded sample of the same workload, same GPU -- BASELINE.md section 2's
+    optional second baseline.  A brute-force O(N^2) sweep with one thread per point and global read-modify-write per
+    MAC; -use_fast_math makes it a timing baseline only (nothing is compared with it except loosely, below)."""
+    import torch
+    import oracle
+    if not oracle.RefGpu.available():
+        return None
+    R = oracle.RefGpu()
+    d = {k: (v[:clouds].contiguous() if k != "filter" else v) for k, v in run.devt.items()}
+    stride = torch.tensor(list(run.stride), dtype=torch.int32, device=run.device)
+    voxel = torch.tensor([VOXEL], dtype=torch.float32, device=run.device)
+    out = torch.empty((clouds, run.N, run.Cout), device=run.device)
+    gi, gf = torch.empty_like(d["input"]), torch.empty_like(d["filter"])
+
+    def step():
+        R.forward(d["points"], d["input"], d["filter"], stride, voxel, out)
+        R.backward(d["grad_out"], d["points"], d["input"], d["filter"], stride, voxel, gi, gf)
+
+    step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()                       # (the op synchronises the device itself, tf_conv3p_atrous.cu:577)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    from pointwise_b200 import NeighborPlan, conv3p_forward
+    mine = conv3p_forward(NeighborPlan(d["points"], run.stride, VOXEL, check="sync"), d["input"], d["filter"])
+    dev = float((mine - out).abs().max() / out.abs().max())
+    return {"value": clouds * run.N / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+            "sample": f"{clouds} clouds x {run.N} points per step, {run.Cin}->{run.Cout}, fwd+bwd, same GPU",
+            "kind": "reference CUDA kernels compiled unmodified for sm_100a (fast-math: timing baseline, not a parity "
+                    "reference)", "forward_max_rel_deviation_from_ours": dev}
 
 
 def net_arm(args, rank, world, device):

@@ -25,6 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(_HERE, "libconv3p_oracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libconv3p_ref.so")
 REF_ST_SO = os.path.join(_HERE, "_ref", "libconv3p_ref_st.so")
+REF_GPU_SO = os.path.join(_HERE, "_ref", "libconv3p_ref_gpu.so")
 NCELL = 27
 
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
@@ -230,6 +231,45 @@ class Ref:
             if total <= cap:
                 return off, j[:total].copy(), f[:total].copy()
             cap = int(total)
+
+
+class RefGpu:
+    """The reference's own GPU op (tf_conv3p_atrous.cu compiled unmodified for sm_100a, ``make -C oracle refgpu``):
+    a TIMING baseline for bench.py ("the reference's GPU code on the same box").  Built with the reference's
+    -use_fast_math, so it is not a parity reference.  Takes CUDA torch tensors."""
+
+    kind = "reference-gpu"
+
+    def __init__(self):
+        if not os.path.exists(REF_GPU_SO):
+            raise FileNotFoundError(REF_GPU_SO)
+        self.lib = L = C.CDLL(REF_GPU_SO)
+        vp = C.c_void_p
+        L.refgpu_conv3p_forward_f32.argtypes = [vp] * 5 + [C.c_int] * 4 + [vp]
+        L.refgpu_conv3p_backward_f32.argtypes = [vp] * 6 + [C.c_int] * 4 + [vp, vp]
+        L.refgpu_last_error.restype = C.c_char_p
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_GPU_SO)
+
+    def forward(self, points, input, filter, stride_dev, voxel_dev, out):
+        B, N, Cin = input.shape
+        rc = self.lib.refgpu_conv3p_forward_f32(points.data_ptr(), input.data_ptr(), filter.data_ptr(),
+                                                stride_dev.data_ptr(), voxel_dev.data_ptr(), B, N, Cin,
+                                                filter.shape[-1], out.data_ptr())
+        if rc:
+            raise RuntimeError(f"reference GPU op failed ({rc}): {self.lib.refgpu_last_error().decode()}")
+        return out
+
+    def backward(self, grad_out, points, input, filter, stride_dev, voxel_dev, grad_input, grad_filter):
+        B, N, Cin = input.shape
+        rc = self.lib.refgpu_conv3p_backward_f32(grad_out.data_ptr(), points.data_ptr(), input.data_ptr(),
+                                                 filter.data_ptr(), stride_dev.data_ptr(), voxel_dev.data_ptr(), B, N,
+                                                 Cin, filter.shape[-1], grad_input.data_ptr(), grad_filter.data_ptr())
+        if rc:
+            raise RuntimeError(f"reference GPU op failed ({rc}): {self.lib.refgpu_last_error().decode()}")
+        return grad_input, grad_filter
 
 
 _port = None

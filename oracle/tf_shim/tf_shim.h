@@ -11,6 +11,9 @@
 //   OP_REQUIRES / OP_REQUIRES_OK / errors::InvalidArgument               :410-443, :583-585
 //   OpKernel, OpKernelConstruction, REGISTER_KERNEL_BUILDER, TF_CALL_*   :396-401, :511-517
 #pragma once
+#ifdef TF_SHIM_GPU
+#include <cuda_runtime.h>
+#endif
 #include <cassert>
 #include <cstdint>
 #include <cstring>
@@ -101,6 +104,15 @@ class Tensor {
 
 class OpKernelConstruction {};
 
+// The reference's GPU op (tf_conv3p_atrous.cu:97-106) takes its scratch memory from
+// context->allocate_temp(DataTypeToEnum<double>::value, shape, &tensor); the shim serves it with cudaMalloc
+// (TF_SHIM_GPU builds only, compiled by nvcc) and frees it when the context dies.
+enum DataType { DT_FLOAT = 1, DT_DOUBLE = 2 };
+template <typename T>
+struct DataTypeToEnum {
+  static const DataType value = DT_DOUBLE;
+};
+
 class OpKernelContext {
  public:
   std::vector<Tensor> inputs;
@@ -123,6 +135,19 @@ class OpKernelContext {
     return Status::OK();
   }
   void SetStatus(const Status& s) { status = s; }
+#ifdef TF_SHIM_GPU
+  std::vector<void*> temps;
+  Status allocate_temp(DataType, const TensorShape& shape, Tensor* out) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)shape.num_elements() * 8 + 16) != cudaSuccess) return Status("cudaMalloc failed");
+    temps.push_back(p);
+    *out = Tensor(shape, p);
+    return Status::OK();
+  }
+  ~OpKernelContext() {
+    for (size_t i = 0; i < temps.size(); ++i) cudaFree(temps[i]);
+  }
+#endif
 };
 
 class OpKernel {

@@ -51,8 +51,9 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaGetDevice");
   std::lock_guard<std::mutex> lock(mu);
-  size_t& have = done[std::make_pair(kernel, dev)];
+  size_t& have = done[std::make_pair(kernel, dev)];   // largest request already served for this (kernel, device)
   if (have >= bytes) return CONV3P_OK;
+  const size_t requested = bytes;
   // static + dynamic shared memory share the 227 KB a CTA may opt in to
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
@@ -61,7 +62,7 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes) {
   if (bytes > limit) bytes = limit;
   e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-  have = bytes;
+  have = requested;
   return CONV3P_OK;
 }
 

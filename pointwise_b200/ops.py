@@ -99,8 +99,13 @@ def _stream_ptr(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-# CONV3P_PREFETCH_BACKWARD=0 keeps the backward lists on the caller's stream (A/B timing)
+# CONV3P_PREFETCH_BACKWARD=0 keeps the backward lists on the caller's stream (A/B timing).  Measured (one B200,
+# fwd+bwd step with / without the side stream): 262,144 points 3.956 / 3.973 ms, 65,536 points 0.833 / 0.864 ms
+# (9->9) and 2.155 / 2.210 ms (36->13) -- but 32,768 points 0.528 / 0.358 ms: below ~50k points the step is so short
+# that the cross-stream hand-off and the allocator's deferred reuse of the plan buffer cost more than the overlap
+# gains, so small batches stay on one stream.
 PREFETCH_BACKWARD = os.environ.get("CONV3P_PREFETCH_BACKWARD", "1") != "0"
+PREFETCH_MIN_POINTS = int(os.environ.get("CONV3P_PREFETCH_MIN_POINTS", "49152"))
 _side_streams = {}
 
 
@@ -377,7 +382,8 @@ class NeighborPlan:
         """Builds the backward lists on a side stream, ordered after the neighbour search only -- called once the
         forward kernels are enqueued, the list kernel fills whatever the persistent forward CTAs leave free instead
         of sitting between forward and backward on the main stream.  ensure_backward() joins it."""
-        if self.has_backward or self._bwd_ready is not None or self.B * self.N == 0 or not PREFETCH_BACKWARD:
+        if (self.has_backward or self._bwd_ready is not None or not PREFETCH_BACKWARD
+                or self.B * self.N < max(1, PREFETCH_MIN_POINTS)):
             return self
         side = _side_stream(self.device)
         side.wait_event(self._searched)

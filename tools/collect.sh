@@ -38,7 +38,7 @@ ncu)
       python bench.py --steps 2 --warmup 3 --no-cpu --no-sweep --no-b16 --no-parity > $O/ncu_launch_$TAG.log 2>&1 ;;
 full)
   timeout 500 ncu --set full --clock-control none --import-source on \
-      -k regex:"k_gather_mma|k_backward_filter|k_neighbor_search|k_backward_lists|k_cloud_sort|k_group_items|k_plan" -s 10 -c 10 -f \
+      -k regex:"k_gather_mma|k_backward_filter|k_neighbor_search|k_backward_lists|k_cloud_sort|k_group_items" -s 8 -c 8 -f \
       -o $O/prof_$TAG python tools/run_once.py 2 > $O/ncu_full_$TAG.log 2>&1
   tail -2 $O/ncu_full_$TAG.log ;;
 sanitize)
