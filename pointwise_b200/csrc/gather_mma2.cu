@@ -90,7 +90,7 @@ struct HalfLists {
 };
 
 template <int ROWS, bool HALF>
-__global__ void __launch_bounds__(ROWS)
+__global__ void __launch_bounds__(ROWS, 512 / ROWS)   // at least 512 threads per SM: caps the registers at 128
 k_group_items(const int* __restrict__ cnt, const long long* __restrict__ begin, const int* __restrict__ len,
               const float4* __restrict__ sorted_xyzi, long long total_points, long long capacity, int N,
               uint2* __restrict__ g_items, int* __restrict__ g_nnz, int* __restrict__ g_rowid,

@@ -291,6 +291,7 @@ k_backward_lists(int B, int N, int sx_, int sy_, int sz_, float voxel, long long
   __shared__ int wcnt[NB_WARPS][32];
   __shared__ int wpre[NB_WARPS][32];
   __shared__ int wrun[NB_WARPS][32];
+  __shared__ uint32_t bstash[NB_WARPS][STASH_CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long qpos = (long long)blockIdx.x * NB_WARPS + warp;
   if (qpos >= (long long)B * N) return;
@@ -326,12 +327,22 @@ k_backward_lists(int B, int N, int sx_, int sy_, int sz_, float voxel, long long
     return members == 0 ? -1 : f;                                           // :679
   };
 
+  // pass 1: cell of every entry, its rank inside the cell (visiting order) and the cell's member count, kept in shared
+  // memory for lists of up to STASH_CAP entries (longer lists re-bin a second time)
+  uint32_t* st = bstash[warp];
   for (int c = 0; c < K; c += 32) {
-    int ii, members;
-    if (c + lane < K) {
-      int f = rebin(c + lane, ii, members);
-      if (f >= 0) atomicAdd(&cnt[f], 1);
-    }
+    int ii = 0, members = 1, f = -1;
+    if (c + lane < K) f = rebin(c + lane, ii, members);
+    const bool hit = f >= 0;
+    const unsigned peers = __match_any_sync(C3P_FULL_MASK, hit ? f : C3P_NCELL);
+    const unsigned before = peers & lanemask_lt();
+    int rank = 0;
+    if (hit) rank = cnt[f] + __popc(before);
+    __syncwarp();
+    if (hit && before == 0u) cnt[f] += __popc(peers);
+    __syncwarp();
+    if (c + lane < K && c + lane < STASH_CAP)   // f (5 bits, 31 = dropped) | rank (9 bits) | members (18 bits, saturating)
+      st[c + lane] = (uint32_t)(hit ? f : 31) | ((uint32_t)rank << 5) | ((uint32_t)min(members, (1 << 18) - 1) << 14);
   }
   __syncwarp();
   const int mine = lane < C3P_NCELL ? cnt[lane] : 0;
@@ -346,13 +357,27 @@ k_backward_lists(int B, int N, int sx_, int sy_, int sz_, float voxel, long long
   const int Kb = __shfl_sync(C3P_FULL_MASK, incl, 31);
   if (lane == 0) atomicAdd((unsigned long long*)&v.header[H_BWD_PAIRS], (unsigned long long)Kb);
   __syncwarp();
-  for (int c = 0; c < K; c += 32) {
-    int ii = 0, members = 1, f = -1;
-    if (c + lane < K) f = rebin(c + lane, ii, members);
-    const int slot = place(f >= 0, f, pre, run);
-    if (f >= 0) {
-      v.bwd_row[begin + slot] = ii;
-      v.bwd_weight[begin + slot] = __fdiv_rn(1.0f, (float)members);
+  if (K <= STASH_CAP) {
+    for (int m = lane; m < K; m += 32) {
+      const uint32_t e = st[m];
+      const int f = (int)(e & 31u);
+      if (f == 31) continue;
+      int members = (int)(e >> 14);
+      const long long slot = begin + pre[f] + (int)((e >> 5) & 511u);
+      const int ii = __ldg(fwd + m);
+      if (members == (1 << 18) - 1) members = __ldg(v.count_table + (size_t)ii * C3P_NCELL + f);   // saturated: re-read
+      v.bwd_row[slot] = ii;
+      v.bwd_weight[slot] = __fdiv_rn(1.0f, (float)members);
+    }
+  } else {
+    for (int c = 0; c < K; c += 32) {
+      int ii = 0, members = 1, f = -1;
+      if (c + lane < K) f = rebin(c + lane, ii, members);
+      const int slot = place(f >= 0, f, pre, run);
+      if (f >= 0) {
+        v.bwd_row[begin + slot] = ii;
+        v.bwd_weight[begin + slot] = __fdiv_rn(1.0f, (float)members);
+      }
     }
   }
 }
