@@ -756,7 +756,7 @@ def run_sweep(L, device, warm=2, steps=5):
     return out
 
 
-def reference_gpu_code(run: Runner, clouds=4, steps=3):
+def reference_gpu_code(run: Runner, clouds=4, steps=2):
     """The reference's own CUDA kernels (tf_conv3p_atrous.cu, compiled unmodified for sm_100a with its own flags:
     oracle/_ref/libconv3p_ref_gpu.so) on a bounded sample of the same workload, same GPU -- BASELINE.md section 2's
     optional second baseline.  A brute-force O(N^2) sweep with one thread per point and global read-modify-write per

@@ -220,7 +220,7 @@ int conv3p_host_backward_f32(const float* h_grad_output, const float* h_points,
 const char* conv3p_status_string(int status);
 const char* conv3p_last_cuda_error(void); /* thread-local text of the last CONV3P_ERR_CUDA */
 int conv3p_abi_version(void);
-/* Number of kernels this library launched on behalf of the calling thread since the last reset. */
+/* Number of kernels this library launched (all threads of the process) since the last reset. */
 long long conv3p_launch_count(int reset);
 /* Selects the contraction engine.  Low three bits: 0 = auto (tensor cores where the shape is a real dense GEMM, else
  * the fp32 engines), 1 = fp32 SIMT only (warp-per-point or tile kernels by channel count), 2 = tensor cores (3xTF32)

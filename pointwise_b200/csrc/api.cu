@@ -15,7 +15,7 @@
 namespace c3p {
 
 static thread_local char g_cuda_error[512] = "";
-static thread_local long long g_launches = 0;
+static std::atomic<long long> g_launches{0};   // process-wide: autograd runs the backward pass on its own thread
 static std::atomic<int> g_engine{0};
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -24,7 +24,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   (void)cudaGetLastError();
   return CONV3P_ERR_CUDA;
 }
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int engine() { return g_engine.load(std::memory_order_relaxed); }
 
 // ---- per-device facts and per-kernel attributes, resolved once ------------------------------------------
@@ -274,9 +274,7 @@ const char* conv3p_status_string(int s) {
 const char* conv3p_last_cuda_error(void) { return g_cuda_error; }
 
 long long conv3p_launch_count(int reset) {
-  long long n = g_launches;
-  if (reset) g_launches = 0;
-  return n;
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 int conv3p_set_engine(int e) { return g_engine.exchange(e); }
