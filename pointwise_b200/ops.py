@@ -192,8 +192,8 @@ class NeighborPlan:
     * the first plan of a (B, N, stride, voxel) shape is built with a synchronous check (one 128-byte read-back,
       rebuilt larger if the guess was too small) and leaves a grow-only estimate with 25 % head-room;
     * every later plan of that shape uses the estimate and only ENQUEUES a copy of the plan's counters into pinned
-      host memory.  The copy is looked at later -- when the backward pass starts, when the next plan is built, or
-      on ``verify()`` / ``stats`` -- by which time it has long arrived.  Should a batch ever exceed the estimate,
+      host memory.  They are looked at later, without waiting -- when the backward pass starts, when the next plan
+      is built -- or on ``verify()`` / ``stats``.  Should a batch ever exceed the estimate,
       the affected outputs were NaN-poisoned on the device (never silently wrong), the estimate is raised and a
       ``Conv3pError(ERR_PAIR_OVERFLOW)`` is raised at that point: rerun the step.
 
@@ -511,7 +511,11 @@ def conv3p_backward(plan: NeighborPlan, grad_output: torch.Tensor, input: torch.
         raise ValueError("backprop grad tensor has wrong size for dim 1")
     if grad_output.shape[2] != Cout:
         raise ValueError("backprop grad tensor has wrong size for dim 2")
-    plan.verify(block=True)      # deferred overflow check of the plan (its copy arrived long ago: no stream sync)
+    # deferred overflow check of the plan: looked at if its counters have arrived (they have when backward runs after a
+    # loss was computed); never waited for -- a caller that enqueues backward right behind forward (bench, the
+    # host-buffer pipeline) would otherwise stall until the plan build has run.  A late flag is raised by the next
+    # plan build, by HostConv3p.fetch() or by plan.verify().
+    plan.verify(block=False)
     plan.ensure_backward()
     L = _lib.lib()
     gi = torch.empty((plan.B, plan.N, Cin), dtype=torch.float32, device=plan.device) \
