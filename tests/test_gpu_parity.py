@@ -639,3 +639,34 @@ def test_bf16_correction_split_against_three_tf32_products(port, Cin, Cout):
     print("max err / sum|terms| (fwd, grad_input, grad_filter): production", errs[0], "3xTF32", errs[512])
     assert not np.array_equal(outs[0], outs[512])
     assert max(errs[0]) < 3e-6, errs          # 3x head-room under the 1e-5 tolerance
+
+
+def test_whole_step_is_cuda_graph_capturable():
+    """Plan build + forward + backward enqueue nothing but stream-ordered work on the caller's stream: the whole step can be
+    captured into a CUDA graph (any host synchronisation or device allocation by the library would abort the capture,
+    SURVEY 8b) and the replay gives bit-identical results."""
+    from pointwise_b200 import NeighborPlan, conv3p_backward, conv3p_forward
+    pr = make_problem(2, 1500, 64, 128, "room", seed=61)
+    P, X, W, G = (dev(pr[k]) for k in ("points", "input", "filter", "grad_out"))
+    cap = int(NeighborPlan(P, 1, V, check="sync").stats.total_pairs * 1.05) + 1024
+
+    def step():
+        plan = NeighborPlan(P, 1, V, check=False, capacity=cap)
+        y = conv3p_forward(plan, X, W)
+        gi, gf = conv3p_backward(plan, G, X, W)
+        return y, gi, gf
+
+    want = step()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        got = step()
+    for t in got:
+        t.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(want, got))
