@@ -247,9 +247,9 @@ int conv3p_debug_w2_cycles(unsigned long long* host16);
 int conv3p_profile_enable(int on);
 long long conv3p_profile_read(char* buf, size_t cap);
 
-/* Self-test of the tensor-core plumbing: D[128,N] = A[128,K] * B[N,K]^T on one CTA with tcgen05
- * (split != 0: 3xTF32 hi/lo split, fp32-class accuracy; split == 0: plain TF32).  N % 16 == 0,
- * 16 <= N <= 256, K % 32 == 0.  Device pointers. */
+/* Self-test of the tensor-core plumbing: D[128,N] = A[128,K] * B[N,K]^T on one CTA with tcgen05.  split: 0 = plain
+ * TF32, 1 = 3xTF32 (hi/lo split, three TF32 products), 1|8 = the production split (TF32 product of the rounded hi
+ * parts + one BF16 chain for the two correction terms).  N % 16 == 0, 16 <= N <= 256, K % 32 == 0.  Device pointers. */
 int conv3p_selftest_tc(const float* A, const float* B, float* D, int N, int K, int split,
                        conv3p_stream_t stream);
 /* Same with the contraction index outermost in memory (MN-major operands, as in the weight-gradient

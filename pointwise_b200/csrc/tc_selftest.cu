@@ -31,10 +31,8 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const bool probe_b32 = (split & 2) != 0;   // hardware probe: K-major operands stored with the 32B-base swizzle
-  const bool probe_m64 = (split & 4) != 0;   // hardware probe: M = 64 (rows 64..127 of A are ignored)
   const bool bf16c = (split & 8) != 0;       // the production split: TF32 main product + BF16 correction products
-  const uint32_t idesc = make_idesc_tf32(probe_m64 ? 64 : 128, N);
+  const uint32_t idesc = make_idesc_tf32(128, N);
   split &= 1;
 
   uint32_t phase = 0;
@@ -47,7 +45,7 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
       if (bf16c) h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
       float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       if (!split) h = v;
-      const uint32_t o = probe_b32 ? panel_chunk_offset_mn(r, c) : panel_chunk_offset(r, c);
+      const uint32_t o = panel_chunk_offset(r, c);
       *reinterpret_cast<float4*>(a_hi + o) = h;
       if (bf16c) {   // A_c = [A_lo | A_hi] as bf16
         *reinterpret_cast<uint2*>(a_lo + panel_offset16(r, 4 * c)) = make_uint2(pack_bf16x2(l.x, l.y), pack_bf16x2(l.z, l.w));
@@ -63,7 +61,7 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
       if (bf16c) h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
       float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       if (!split) h = v;
-      const uint32_t o = probe_b32 ? panel_chunk_offset_mn(r, c) : panel_chunk_offset(r, c);
+      const uint32_t o = panel_chunk_offset(r, c);
       *reinterpret_cast<float4*>(b_hi + o) = h;
       if (bf16c) {   // B_c = [B_hi | B_lo] as bf16
         *reinterpret_cast<uint2*>(b_lo + panel_offset16(r, 4 * c)) = make_uint2(pack_bf16x2(h.x, h.y), pack_bf16x2(h.z, h.w));
@@ -76,10 +74,8 @@ k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B, float* _
     __syncthreads();
     if (tid == 0) {
       tc_fence_after_sync();
-      // probe: same K-major descriptor, layout type SWIZZLE_128B_BASE32B (1) instead of SWIZZLE_128B (2)
-      const uint64_t lt = probe_b32 ? ((uint64_t)1 << 61) ^ ((uint64_t)2 << 61) : 0;
-      const uint64_t dah = make_smem_desc(smem_u32(a_hi)) ^ lt, dal = make_smem_desc(smem_u32(a_lo)) ^ lt;
-      const uint64_t dbh = make_smem_desc(smem_u32(b_hi)) ^ lt, dbl = make_smem_desc(smem_u32(b_lo)) ^ lt;
+      const uint64_t dah = make_smem_desc(smem_u32(a_hi)), dal = make_smem_desc(smem_u32(a_lo));
+      const uint64_t dbh = make_smem_desc(smem_u32(b_hi)), dbl = make_smem_desc(smem_u32(b_lo));
 #pragma unroll
       for (int ks = 0; ks < PANEL_K / UMMA_K; ++ks) {
         const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
