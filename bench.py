@@ -112,6 +112,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def ready(self, timeout=3.0):
+        """Block until the first sample arrived: nvidia-smi attaching to the GPU stalls launches for tens of ms, which
+        must not fall into the timed region (a 16-cloud step showed 5.2 ms instead of 1.2 ms when it did)."""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout and self.proc.poll() is None:
+            time.sleep(0.01)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -579,6 +586,8 @@ def gpu_arm(args):
     for _ in range(warm):
         run.step()
     run.join()
+    if rank == 0:
+        sampler.ready()
     # the reported step time is taken WITHOUT the per-kernel event pairs (two cudaEventRecord per launch open small gaps
     # between dependent kernels); the per-kernel breakdown comes from a second, instrumented pass over the same steps
     ms_step = timed(run.step, args.steps, world, device, finish=run.join)
