@@ -199,6 +199,22 @@ int conv3p_op_backward_f32(const float* grad_output, const float* points, const 
                            long long pair_capacity, float* grad_input, float* grad_filter,
                            void* workspace, size_t workspace_bytes, conv3p_stream_t stream);
 
+/* ---- T = double ----------------------------------------------------------------------------------
+ * The reference registers Conv3p / Conv3pGrad for double as well (register_op.cpp:45, 64; CPU kernels
+ * tf_conv3p_atrous.cpp:516, 727): points, input, filter, voxel size and the outputs in double, the whole neighbour
+ * predicate evaluated in double (:239-290, :654-679).  One-shot calls, every filter shape up to 512 cells (3x3x3
+ * included), fp64 SIMT; same status codes and NaN poisoning on pair overflow as the float calls.  `geom` of the
+ * workspace query carries (float)voxel_size. */
+size_t conv3p_op_workspace_bytes_f64(const conv3p_geom_t* geom, const int filter_dims[3], int Cin, int Cout);
+int conv3p_op_forward_f64(const double* points, const double* input, const double* filter, const int filter_dims[3],
+                          const int stride_xyz[3], double voxel_size, int B, int N, int Cin, int Cout,
+                          long long pair_capacity, double* output, void* workspace, size_t workspace_bytes,
+                          conv3p_stream_t stream);
+int conv3p_op_backward_f64(const double* grad_output, const double* points, const double* input, const double* filter,
+                           const int filter_dims[3], const int stride_xyz[3], double voxel_size, int B, int N, int Cin,
+                           int Cout, long long pair_capacity, double* grad_input, double* grad_filter, void* workspace,
+                           size_t workspace_bytes, conv3p_stream_t stream);
+
 /* ---- host-buffer calls (the reference's feed/fetch shape) -------------------------------------- */
 /* All tensor pointers are HOST pointers (pinned memory gives asynchronous copies); `workspace` is
  * DEVICE memory >= conv3p_host_workspace_bytes().  Copies inputs host->device, runs the operator,

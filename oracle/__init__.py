@@ -29,6 +29,7 @@ REF_GPU_SO = os.path.join(_HERE, "_ref", "libconv3p_ref_gpu.so")
 NCELL = 27
 
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
 
@@ -44,6 +45,10 @@ def build(verbose: bool = False) -> None:
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
 
 
 def _stride3(stride):
@@ -163,6 +168,12 @@ class Ref:
         L.ref_neighbors_f32.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_float,
                                         _i64p, _i32p, _i32p, C.c_longlong]
         L.ref_neighbors_f32.restype = C.c_longlong
+        if hasattr(L, "ref_conv3p_forward_f64"):
+            L.ref_conv3p_forward_f64.argtypes = [_f64p, _f64p, _f64p, _i32p, _f64p] + [C.c_int] * 7 + [_f64p]
+            L.ref_conv3p_backward_f64.argtypes = [_f64p, _f64p, _f64p, _f64p, _i32p, _f64p] + [C.c_int] * 7 + \
+                [_f64p, _f64p]
+            L.ref_neighbor_count_f64.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_double, _i32p]
+            L.ref_neighbor_count_f64.restype = None
 
     @staticmethod
     def available() -> bool:
@@ -216,6 +227,38 @@ class Ref:
         fz, fy, fx = (int(d) for d in dims)
         out = np.zeros((n, fz * fy * fx), np.int32)
         self.lib.ref_neighbor_count_f32(xyz, n, fz, fy, fx, _stride3(stride), float(np.float32(voxel)), out)
+        return out
+
+    # ---- T = double (register_op.cpp:45, 64; tf_conv3p_atrous.cpp:516, 727) ---------------------------------
+    def forward64(self, points, input, filter, stride, voxel):
+        points, input, filter = _f64(points), _f64(input), _f64(filter)
+        B, N = points.shape[0], points.shape[1]
+        fz, fy, fx, Cin, Cout = filter.shape
+        out = np.zeros((B, N, Cout), np.float64)
+        rc = self.lib.ref_conv3p_forward_f64(points, input, filter, _stride3(stride), np.array([voxel], np.float64),
+                                             B, N, Cin, Cout, fz, fy, fx, out)
+        if rc:
+            raise ValueError(self._err())
+        return out
+
+    def backward64(self, grad_out, points, input, filter, stride, voxel):
+        grad_out, points, input, filter = _f64(grad_out), _f64(points), _f64(input), _f64(filter)
+        B, N = points.shape[0], points.shape[1]
+        fz, fy, fx, Cin, Cout = filter.shape
+        gi = np.zeros((B, N, Cin), np.float64)
+        gf = np.zeros(filter.shape, np.float64)
+        rc = self.lib.ref_conv3p_backward_f64(grad_out, points, input, filter, _stride3(stride),
+                                              np.array([voxel], np.float64), B, N, Cin, Cout, fz, fy, fx, gi, gf)
+        if rc:
+            raise ValueError(self._err())
+        return gi, gf
+
+    def neighbor_count64(self, xyz, stride, voxel, dims=(3, 3, 3)):
+        xyz = _f64(xyz).reshape(-1, 3)
+        n = xyz.shape[0]
+        fz, fy, fx = (int(d) for d in dims)
+        out = np.zeros((n, fz * fy * fx), np.int32)
+        self.lib.ref_neighbor_count_f64(xyz, n, fz, fy, fx, _stride3(stride), float(voxel), out)
         return out
 
     def neighbors(self, xyz, stride, voxel):

@@ -136,4 +136,58 @@ long long ref_neighbors_f32(const float* points, int N, int fz, int fy, int fx, 
   return total;
 }
 
+// ---- T = double: the reference registers Conv3p / Conv3pGrad for double as well (register_op.cpp:45, 64;
+// tf_conv3p_atrous.cpp:516, 727).  Same schema order, every floating-point tensor in double. ----------------------
+int ref_conv3p_forward_f64(const double* points, const double* input, const double* filter, const int* stride,
+                           const double* voxel, int B, int N, int Cin, int Cout, int fz, int fy, int fx,
+                           double* output) {
+  using namespace tensorflow;
+  std::unique_ptr<OpKernel> k(CreateKernel<double>("Conv3p", DEVICE_CPU));
+  if (!k) {
+    g_last_error = "Conv3p/CPU/double not registered";
+    return 2;
+  }
+  OpKernelContext ctx;
+  ctx.elem_bytes = sizeof(double);
+  ctx.inputs.push_back(wrap(points, {B, N, 3}));
+  ctx.inputs.push_back(wrap(input, {B, N, Cin}));
+  ctx.inputs.push_back(wrap(filter, {fz, fy, fx, Cin, Cout}));
+  ctx.inputs.push_back(wrap(stride, {3}));
+  ctx.inputs.push_back(wrap(voxel, {1}));
+  ctx.out_buffers.push_back(output);
+  k->Compute(&ctx);
+  return finish(ctx);
+}
+
+int ref_conv3p_backward_f64(const double* grad_out, const double* points, const double* input, const double* filter,
+                            const int* stride, const double* voxel, int B, int N, int Cin, int Cout, int fz, int fy,
+                            int fx, double* grad_input, double* grad_filter) {
+  using namespace tensorflow;
+  std::unique_ptr<OpKernel> k(CreateKernel<double>("Conv3pGrad", DEVICE_CPU));
+  if (!k) {
+    g_last_error = "Conv3pGrad/CPU/double not registered";
+    return 2;
+  }
+  OpKernelContext ctx;
+  ctx.elem_bytes = sizeof(double);
+  ctx.inputs.push_back(wrap(grad_out, {B, N, Cout}));
+  ctx.inputs.push_back(wrap(points, {B, N, 3}));
+  ctx.inputs.push_back(wrap(input, {B, N, Cin}));
+  ctx.inputs.push_back(wrap(filter, {fz, fy, fx, Cin, Cout}));
+  ctx.inputs.push_back(wrap(stride, {3}));
+  ctx.inputs.push_back(wrap(voxel, {1}));
+  ctx.out_buffers.push_back(grad_input);
+  ctx.out_buffers.push_back(grad_filter);
+  k->Compute(&ctx);
+  return finish(ctx);
+}
+
+// Count table of ONE cloud through Grid<CpuAlloc, double>::neighbor_count.
+void ref_neighbor_count_f64(const double* points, int N, int fz, int fy, int fx, const int* stride, double voxel,
+                            int* count) {
+  Grid<CpuAlloc, double> grid(Array<CpuAlloc, double>(const_cast<double*>(points), N), voxel);
+  Array<CpuAlloc, int> cnt(count, N * fz * fy * fx);
+  grid.neighbor_count(fx, fy, fz, stride[0], stride[1], stride[2], voxel, cnt);
+}
+
 }  // extern "C"

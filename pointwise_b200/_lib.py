@@ -24,6 +24,7 @@ EXPORTS = [
     "conv3p_plan_bytes", "conv3p_plan_layout", "conv3p_plan_build_f32", "conv3p_plan_build_backward",
     "conv3p_plan_stats", "conv3p_plan_publish_stats", "conv3p_scratch_bytes", "conv3p_backward_scratch_bytes", "conv3p_forward_f32", "conv3p_forward_ex_f32", "conv3p_selu_backward_f32", "conv3p_backward_f32",
     "conv3p_op_workspace_bytes", "conv3p_op_workspace_bytes_ex", "conv3p_op_backward_workspace_bytes", "conv3p_op_forward_f32", "conv3p_op_backward_f32",
+    "conv3p_op_workspace_bytes_f64", "conv3p_op_forward_f64", "conv3p_op_backward_f64",
     "conv3p_host_workspace_bytes", "conv3p_host_forward_f32", "conv3p_host_backward_f32",
     "conv3p_status_string", "conv3p_last_cuda_error", "conv3p_abi_version", "conv3p_launch_count",
     "conv3p_set_engine", "conv3p_profile_enable", "conv3p_profile_read",
@@ -85,6 +86,11 @@ def _declare(L):
     L.conv3p_op_backward_workspace_bytes.restype = sz
     L.conv3p_op_forward_f32.argtypes = [vp, vp, vp, i3, i3, f, i, i, i, i, ll, vp, vp, sz, vp]
     L.conv3p_op_backward_f32.argtypes = [vp, vp, vp, vp, i3, i3, f, i, i, i, i, ll, vp, vp, vp, sz, vp]
+    d = C.c_double
+    L.conv3p_op_workspace_bytes_f64.argtypes = [gp, i3, i, i]
+    L.conv3p_op_workspace_bytes_f64.restype = sz
+    L.conv3p_op_forward_f64.argtypes = [vp, vp, vp, i3, i3, d, i, i, i, i, ll, vp, vp, sz, vp]
+    L.conv3p_op_backward_f64.argtypes = [vp, vp, vp, vp, i3, i3, d, i, i, i, i, ll, vp, vp, vp, sz, vp]
     L.conv3p_host_workspace_bytes.argtypes = [gp, i, i]
     L.conv3p_host_workspace_bytes.restype = sz
     L.conv3p_host_forward_f32.argtypes = [vp, vp, vp, i3, f, i, i, i, i, ll, vp, vp, sz, vp]

@@ -563,6 +563,46 @@ size_t conv3p_op_workspace_bytes_ex(const conv3p_geom_t* geom, const int filter_
   return generic_workspace_bytes(geom, filter_dims, Cin, Cout);
 }
 
+// ---- T = double (register_op.cpp:45, 64; tf_conv3p_atrous.cpp:516, 727): one-shot calls on the general path --------
+static int check_f64(const int filter_dims[3], const int stride_xyz[3], double voxel_size, int B, int N, int Cin,
+                     int Cout, long long pair_capacity, conv3p_geom_t* g) {
+  if (!filter_dims || !stride_xyz) return CONV3P_ERR_INVALID_ARGUMENT;
+  if (filter_dims[0] < 1 || filter_dims[1] < 1 || filter_dims[2] < 1) return CONV3P_ERR_INVALID_ARGUMENT;
+  if (!generic_filter_supported(filter_dims)) return CONV3P_ERR_UNSUPPORTED;
+  if (!(voxel_size > 0.0) || !((float)voxel_size > 0.f)) return CONV3P_ERR_INVALID_ARGUMENT;
+  *g = make_geom(B, N, stride_xyz, (float)voxel_size, pair_capacity);   // float cell size of the candidate grid only
+  int st = check_geom(g);
+  if (st) return st;
+  return check_channels(Cin, Cout);
+}
+
+size_t conv3p_op_workspace_bytes_f64(const conv3p_geom_t* geom, const int filter_dims[3], int Cin, int Cout) {
+  if (!filter_dims) return 0;
+  return generic_workspace_bytes(geom, filter_dims, Cin, Cout, 8);
+}
+
+int conv3p_op_forward_f64(const double* points, const double* input, const double* filter, const int filter_dims[3],
+                          const int stride_xyz[3], double voxel_size, int B, int N, int Cin, int Cout,
+                          long long pair_capacity, double* output, void* workspace, size_t workspace_bytes,
+                          conv3p_stream_t stream) {
+  conv3p_geom_t g;
+  const int st = check_f64(filter_dims, stride_xyz, voxel_size, B, N, Cin, Cout, pair_capacity, &g);
+  if (st) return st;
+  return generic_forward_f64(&g, filter_dims, voxel_size, points, input, filter, Cin, Cout, output, workspace,
+                             workspace_bytes, stream);
+}
+
+int conv3p_op_backward_f64(const double* grad_output, const double* points, const double* input, const double* filter,
+                           const int filter_dims[3], const int stride_xyz[3], double voxel_size, int B, int N, int Cin,
+                           int Cout, long long pair_capacity, double* grad_input, double* grad_filter, void* workspace,
+                           size_t workspace_bytes, conv3p_stream_t stream) {
+  conv3p_geom_t g;
+  const int st = check_f64(filter_dims, stride_xyz, voxel_size, B, N, Cin, Cout, pair_capacity, &g);
+  if (st) return st;
+  return generic_backward_f64(&g, filter_dims, voxel_size, grad_output, points, input, filter, Cin, Cout, grad_input,
+                              grad_filter, workspace, workspace_bytes, stream);
+}
+
 int conv3p_op_forward_f32(const float* points, const float* input, const float* filter,
                           const int filter_dims[3], const int stride_xyz[3], float voxel_size, int B,
                           int N, int Cin, int Cout, long long pair_capacity, float* output,

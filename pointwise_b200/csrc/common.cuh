@@ -151,9 +151,16 @@ int launch_backward_filter2(const conv3p_geom_t* g, const PlanView& v, const flo
                             cudaStream_t stream, const float* g_store = nullptr, bool items_ready = false);
 int backward_filter2_tile_rows(int N, long long capacity, int Cin, int Cout);   // 64 or 32 (0: shape not supported)
 
-// general filter shapes (generic_filter.cu): any fz x fy x fx with at most 512 cells, fp32 SIMT, one-shot calls
+// general filter shapes (generic_filter.cu): any fz x fy x fx with at most 512 cells, SIMT, one-shot calls; the same
+// kernels instantiated for double serve the reference's T = double registration (every shape, 3x3x3 included)
 bool generic_filter_supported(const int dims_zyx[3]);
-size_t generic_workspace_bytes(const conv3p_geom_t* g, const int dims_zyx[3], int Cin, int Cout);
+size_t generic_workspace_bytes(const conv3p_geom_t* g, const int dims_zyx[3], int Cin, int Cout, int elem_bytes = 4);
+int generic_forward_f64(const conv3p_geom_t* g, const int dims_zyx[3], double voxel, const double* points,
+                        const double* input, const double* filter, int Cin, int Cout, double* output, void* ws,
+                        size_t ws_bytes, cudaStream_t stream);
+int generic_backward_f64(const conv3p_geom_t* g, const int dims_zyx[3], double voxel, const double* grad_out,
+                         const double* points, const double* input, const double* filter, int Cin, int Cout,
+                         double* grad_input, double* grad_filter, void* ws, size_t ws_bytes, cudaStream_t stream);
 int generic_forward(const conv3p_geom_t* g, const int dims_zyx[3], const float* points, const float* input,
                     const float* filter, int Cin, int Cout, float* output, void* ws, size_t ws_bytes,
                     cudaStream_t stream);

@@ -67,14 +67,21 @@ def parse_voxel(voxel_size) -> float:
     return v
 
 
-def _check_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+def _check_cuda_f32(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"Conv3p: {name} must be a torch.Tensor")
     if not t.is_cuda:
         raise RuntimeError(f"Conv3p: {name} must be a CUDA tensor (pointwise_b200 has no CPU fallback)")
-    if t.dtype != torch.float32:
-        raise TypeError(f"Conv3p: {name} must be float32 (got {t.dtype})")
+    if t.dtype != dtype:
+        what = "float32" if dtype == torch.float32 else "float64 like the other tensors of the call"
+        raise TypeError(f"Conv3p: {name} must be {what} (got {t.dtype})")
     return t.contiguous()
+
+
+def _op_dtype(points) -> torch.dtype:
+    """T of the call (register_op.cpp:45: {float, double}): float64 when the points are float64 -- every tensor of the
+    call must then be float64, as in the reference where one attribute T types them all."""
+    return torch.float64 if isinstance(points, torch.Tensor) and points.dtype == torch.float64 else torch.float32
 
 
 def validate(points, input, kernel):
@@ -574,20 +581,23 @@ class _Conv3pFunction(torch.autograd.Function):
 _generic_capacity_hint: dict = {}
 
 
-def _generic_call(points, stride, voxel, dims, Cin, Cout, backward, run):
+def _generic_call(points, stride, voxel, dims, Cin, Cout, backward, run, f64=False):
     """Runs a one-shot C entry point on a workspace sized for `capacity` pairs; grows the capacity and retries when
     the neighbour lists overflowed (one 128-byte read-back per call: this path is the reference-compatible fallback
     for filter shapes no model uses, not the tuned one)."""
     L = _lib.lib()
     B, N = int(points.shape[0]), int(points.shape[1])
-    key = (B, N, stride, voxel, dims)
+    key = (B, N, stride, voxel, dims, f64)
     vol = dims[0] * dims[1] * dims[2]
     cap = _generic_capacity_hint.get(key, max(1024, 2 * vol * B * N))
     dims_c = (C.c_int * 3)(*dims)
     stride_c = (C.c_int * 3)(*stride)
     while True:
         geom = _lib.make_geom(B, N, stride, voxel, cap)
-        nbytes = L.conv3p_op_workspace_bytes_ex(geom, dims_c, Cin, Cout, 1 if backward else 0)
+        if f64:
+            nbytes = L.conv3p_op_workspace_bytes_f64(geom, dims_c, Cin, Cout)
+        else:
+            nbytes = L.conv3p_op_workspace_bytes_ex(geom, dims_c, Cin, Cout, 1 if backward else 0)
         if nbytes == 0:
             raise _lib.Conv3pError(_lib.ERR_UNSUPPORTED, f"filter shape {dims} is not supported (more than 512 cells)")
         ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device)
@@ -607,11 +617,12 @@ class _Conv3pGenericFunction(torch.autograd.Function):
         dims = tuple(int(d) for d in kernel.shape[:3])
         Cin, Cout = int(kernel.shape[3]), int(kernel.shape[4])
         B, N = int(points.shape[0]), int(points.shape[1])
-        out = torch.empty((B, N, Cout), dtype=torch.float32, device=points.device)
+        f64 = points.dtype == torch.float64
+        out = torch.empty((B, N, Cout), dtype=points.dtype, device=points.device)
         _generic_call(points, stride, voxel, dims, Cin, Cout, False,
-                      lambda L, d, s, cap, ws, nb: L.conv3p_op_forward_f32(
+                      lambda L, d, s, cap, ws, nb: (L.conv3p_op_forward_f64 if f64 else L.conv3p_op_forward_f32)(
                           _ptr(points), _ptr(input), _ptr(kernel), d, s, voxel, B, N, Cin, Cout, cap, _ptr(out),
-                          _ptr(ws), nb, _stream_ptr(points.device)))
+                          _ptr(ws), nb, _stream_ptr(points.device)), f64=f64)
         ctx.save_for_backward(points, input, kernel)
         ctx.geometry = (stride, voxel)
         return out
@@ -620,16 +631,17 @@ class _Conv3pGenericFunction(torch.autograd.Function):
     def backward(ctx, grad_output):
         points, input, kernel = ctx.saved_tensors
         stride, voxel = ctx.geometry
-        grad_output = _check_cuda_f32(grad_output, "grad_output")
+        f64 = points.dtype == torch.float64
+        grad_output = _check_cuda_f32(grad_output, "grad_output", points.dtype)
         dims = tuple(int(d) for d in kernel.shape[:3])
         Cin, Cout = int(kernel.shape[3]), int(kernel.shape[4])
         B, N = int(points.shape[0]), int(points.shape[1])
         gi = torch.empty_like(input)
         gf = torch.empty_like(kernel)
         _generic_call(points, stride, voxel, dims, Cin, Cout, True,
-                      lambda L, d, s, cap, ws, nb: L.conv3p_op_backward_f32(
+                      lambda L, d, s, cap, ws, nb: (L.conv3p_op_backward_f64 if f64 else L.conv3p_op_backward_f32)(
                           _ptr(grad_output), _ptr(points), _ptr(input), _ptr(kernel), d, s, voxel, B, N, Cin, Cout, cap,
-                          _ptr(gi), _ptr(gf), _ptr(ws), nb, _stream_ptr(points.device)))
+                          _ptr(gi), _ptr(gf), _ptr(ws), nb, _stream_ptr(points.device)), f64=f64)
         return None, gi, gf, None, None
 
 
@@ -644,16 +656,19 @@ def conv3p(points_tensor, input_tensor, kernel_tensor, stride, voxel_size,
     stride and voxel size (e.g. across layers).  ``activation="selu"`` returns ``selu(conv3p(...))`` with the
     activation fused into the kernel's epilogue (and its derivative applied to the incoming gradient in backward).
     """
-    points = _check_cuda_f32(points_tensor, "points")
-    input = _check_cuda_f32(input_tensor, "input")
-    kernel = _check_cuda_f32(kernel_tensor, "kernel")
+    T = _op_dtype(points_tensor)
+    points = _check_cuda_f32(points_tensor, "points", T)
+    input = _check_cuda_f32(input_tensor, "input", T)
+    kernel = _check_cuda_f32(kernel_tensor, "kernel", T)
     validate(points, input, kernel)
     s, v = parse_stride(stride), parse_voxel(voxel_size)
     if activation not in ACTIVATIONS:
         raise ValueError(f"Conv3p: unknown activation {activation!r}")
-    if tuple(kernel.shape[:3]) != (3, 3, 3):
-        # the reference is generic in the filter shape (tf_conv3p_atrous.cpp:425-427); anything but 3x3x3 takes the
-        # general fp32 path (no plan reuse, no fused epilogue)
+    if tuple(kernel.shape[:3]) != (3, 3, 3) or T == torch.float64:
+        # the reference is generic in the filter shape (tf_conv3p_atrous.cpp:425-427) and registered for double as well
+        # (register_op.cpp:45); anything but float32 3x3x3 takes the general path (no plan reuse, no fused epilogue)
+        if plan is not None:
+            raise ValueError("Conv3p: a NeighborPlan serves float32 3x3x3 filters only")
         y = _Conv3pGenericFunction.apply(points, input, kernel, s, v)
         return torch.nn.functional.selu(y) if activation == "selu" else y
     if plan is None:
@@ -667,12 +682,13 @@ def conv3p_grad(grad_from_next, points, input, filter, stride, voxel_size,
                 plan: Optional[NeighborPlan] = None):
     """Mirror of the reference's ``conv3p_grad`` op (register_op.cpp:63-75):
     -> (input_grad, filter_grad)."""
-    points = _check_cuda_f32(points, "points")
-    input = _check_cuda_f32(input, "input")
-    filter = _check_cuda_f32(filter, "filter")
+    T = _op_dtype(points)
+    points = _check_cuda_f32(points, "points", T)
+    input = _check_cuda_f32(input, "input", T)
+    filter = _check_cuda_f32(filter, "filter", T)
     validate(points, input, filter)
     s, v = parse_stride(stride), parse_voxel(voxel_size)
-    if tuple(filter.shape[:3]) != (3, 3, 3):
+    if tuple(filter.shape[:3]) != (3, 3, 3) or T == torch.float64:
         class _Ctx:      # the autograd node's backward, called directly
             pass
         ctx = _Ctx()

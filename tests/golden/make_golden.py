@@ -46,6 +46,50 @@ GENERAL = {
     "gen_111": (1, 128, 5, 6, (1, 1, 1), (1, 1, 1), "cube", None, 25),
 }
 
+# T = double (register_op.cpp:45, 64; CPU kernels tf_conv3p_atrous.cpp:516, 727):
+# name: (B, N, Cin, Cout, (fz, fy, fx), stride, dist or "lattice", seed)
+DOUBLE = {
+    "f64_333_s1": (2, 300, 3, 4, (3, 3, 3), (1, 1, 1), "room", 41),
+    "f64_333_aniso": (1, 350, 2, 3, (3, 3, 3), (1, 2, 3), "sphere", 42),
+    "f64_222": (2, 200, 3, 2, (2, 2, 2), (1, 1, 1), "cube", 43),
+    # 7x7x7 lattice at half-voxel spacing, every coordinate moved by a double far below float resolution: in exact
+    # arithmetic most points sit on cell boundaries, and only the double bits decide on which side
+    "f64_333_subfloat": (1, 343, 2, 2, (3, 3, 3), (1, 1, 1), "lattice", 44),
+}
+
+
+def run64(R, points, inp, filt, gout, stride):
+    v = 0.1
+    out = R.forward64(points, inp, filt, stride, v)
+    gi, gf = R.backward64(gout, points, inp, filt, stride, v)
+    cnt = np.stack([R.neighbor_count64(points[b], stride, v, dims=filt.shape[:3]) for b in range(points.shape[0])])
+    return dict(points=points, input=inp, filter=filt, grad_out=gout,
+                stride=np.asarray(np.broadcast_to(stride, (3,)), np.int32), voxel=np.float64(v),
+                output=out, grad_input=gi, grad_filter=gf, count_table=cnt)
+
+
+def main64():
+    R = oracle.Ref(single_thread=True)
+    for name, (B, N, Ci, Co, dims, s, dist, seed) in DOUBLE.items():
+        rng = np.random.default_rng(seed)
+        if dist == "lattice":
+            g = np.arange(7, dtype=np.float64) * 0.05 + 0.1
+            P = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(1, -1, 3)
+            P = P + rng.uniform(-1e-11, 1e-11, P.shape)
+            P = P[:, rng.permutation(P.shape[1])]
+        else:
+            P = make_problem(B, N, Ci, Co, dist, seed=seed)["points"].astype(np.float64)
+            P = P + rng.uniform(-1e-8, 1e-8, P.shape)
+        X = rng.uniform(-1, 1, (B, N, Ci))
+        W = rng.uniform(-0.1, 0.1, (*dims, Ci, Co))
+        G = rng.uniform(-1, 1, (B, N, Co))
+        fix = run64(R, P, X, W, G, s)
+        if dist == "lattice":    # the fixture must tell a float predicate from a double one
+            c32 = R.neighbor_count(P[0].astype(np.float32), s, np.float32(0.1), dims=dims)
+            assert not np.array_equal(c32, fix["count_table"][0]), "lattice fixture does not discriminate"
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **fix)
+    print("wrote", len(DOUBLE), "double fixtures to", HERE)
+
 
 def run(R, points, inp, filt, gout, stride):
     out = R.forward(points, inp, filt, stride, V)
@@ -77,4 +121,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["f64"]:      # only the double fixtures (the float ones stay byte-identical in git)
+        main64()
+    else:
+        main()
+        main64()

@@ -12,9 +12,11 @@ from pointwise_b200.synth import make_problem
 
 GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
 GOLDEN = sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                if not os.path.basename(p).startswith(("augment_", "gen_")))
+                if not os.path.basename(p).startswith(("augment_", "gen_", "f64_")))
 # filter shapes other than 3x3x3: the C port restates the 3x3x3 case only; these vectors pin the general CUDA path
 GENERAL = sorted(glob.glob(os.path.join(GOLDEN_DIR, "gen_*.npz")))
+# T = double (register_op.cpp:45, 64): vectors from the reference's double kernels pin the CUDA double path
+DOUBLE = sorted(glob.glob(os.path.join(GOLDEN_DIR, "f64_*.npz")))
 AUGMENT = sorted(glob.glob(os.path.join(GOLDEN_DIR, "augment_*.npz")))
 V = 0.1
 
@@ -164,3 +166,34 @@ def test_general_shape_vectors_are_the_references_output(path):
     assert np.array_equal(gi, g["grad_input"]) and np.array_equal(gf, g["grad_filter"])
     for b in range(B):
         assert np.array_equal(R.neighbor_count(g["points"][b], stride, V, dims=(fz, fy, fx)), g["count_table"][b])
+
+
+@pytest.mark.parametrize("path", DOUBLE, ids=[os.path.basename(p)[:-4] for p in DOUBLE])
+def test_double_vectors_are_the_references_output(path):
+    """The f64_* fixtures reproduce when the reference's double kernels (tf_conv3p_atrous.cpp:516, 727) are run again
+    on their inputs -- wherever oracle/_ref is present; dtypes and shapes are checked anywhere.  The 3x3x3 ones are
+    also close to what the float port computes on the rounded inputs, except where only the double bits decide."""
+    import oracle
+    g = np.load(path)
+    fz, fy, fx, Cin, Cout = g["filter"].shape
+    B, N = g["points"].shape[:2]
+    for k in ("points", "input", "filter", "grad_out", "output", "grad_input", "grad_filter"):
+        assert g[k].dtype == np.float64, k
+    assert g["count_table"].shape == (B, N, fz * fy * fx) and g["output"].shape == (B, N, Cout)
+    stride = tuple(int(s) for s in g["stride"])
+    if (fz, fy, fx) == (3, 3, 3) and "subfloat" not in path:
+        oracle.build()
+        o32 = oracle.port().forward(g["points"].astype(np.float32), g["input"].astype(np.float32),
+                                    g["filter"].astype(np.float32), stride, np.float32(0.1))
+        # float rounding moves a few points across cell boundaries; the bulk agrees
+        close = np.isclose(o32, g["output"], rtol=1e-3, atol=1e-4)
+        assert close.mean() > 0.98
+    if not oracle.Ref.available():
+        pytest.skip("oracle/_ref not built here")
+    R = oracle.Ref(single_thread=True)
+    assert np.array_equal(R.forward64(g["points"], g["input"], g["filter"], stride, float(g["voxel"])), g["output"])
+    gi, gf = R.backward64(g["grad_out"], g["points"], g["input"], g["filter"], stride, float(g["voxel"]))
+    assert np.array_equal(gi, g["grad_input"]) and np.array_equal(gf, g["grad_filter"])
+    for b in range(B):
+        assert np.array_equal(R.neighbor_count64(g["points"][b], stride, float(g["voxel"]), dims=(fz, fy, fx)),
+                              g["count_table"][b])

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round collection on the GPU box.  usage: gpurun --timeout 1500 -- 'bash tools/collect.sh <tag> [stage ...]'
-# stages: test bench ref layers nets ncu full tf32 sanitize timing (default: test bench)
+# stages: test testall bench benchq ref layers nets ncu full tf32 f64 sanitize timing (default: test bench)
 TAG=${1:-r2}
 shift
 STAGES=${@:-test bench}
@@ -41,6 +41,8 @@ full)
       -k regex:"k_gather_mma|k_backward_filter|k_neighbor_search|k_backward_lists|k_cloud_sort|k_group_items" -s 8 -c 8 -f \
       -o $O/prof_$TAG python tools/run_once.py 2 > $O/ncu_full_$TAG.log 2>&1
   tail -2 $O/ncu_full_$TAG.log ;;
+f64)
+  timeout 300 python tools/f64_timing.py > $O/f64_timing_$TAG.json 2> $O/f64_timing_$TAG.err; cat $O/f64_timing_$TAG.json ;;
 sanitize)
   timeout 900 bash tools/sanitize.sh $TAG ;;
 esac
