@@ -18,9 +18,10 @@
  *   filter  [3,3,3,Cin,Cout] float32, dims ordered z,y,x; weight index (f*Cin+k)*Cout+c,
  *           f = (fz*3+fy)*3+fx                    output  [B,N,Cout] float32
  *   stride  int[3] in x,y,z order                 voxel_size  float
- * float32 only.  3x3x3 filters (every reference model) run on the tuned engines through the plan calls below; other
- * filter shapes (the reference reads fz, fy, fx from the tensor, tf_conv3p_atrous.cpp:425-427) are served by the
- * one-shot conv3p_op_* calls on a general fp32 path (up to 512 cells).
+ * float32 3x3x3 filters (every reference model) run on the tuned engines through the plan calls below; other filter
+ * shapes (the reference reads fz, fy, fx from the tensor, tf_conv3p_atrous.cpp:425-427) are served by the one-shot
+ * conv3p_op_* calls on a general path (up to 512 cells), and so is the reference's T = double registration
+ * (register_op.cpp:45, 64): conv3p_op_*_f64, every tensor in double.
  *
  * Memory: the library never allocates device memory.  The caller owns inputs, outputs, the plan
  * buffer and the scratch buffer (sizes from the *_bytes functions).  Outputs are fully overwritten.

@@ -652,7 +652,9 @@ def conv3p(points_tensor, input_tensor, kernel_tensor, stride, voxel_size,
     points [B,N,3], input [B,N,Cin], kernel [fz,fy,fx,Cin,Cout] (z,y,x,in,out; 3x3x3 in every reference model and on
     the tuned engines, any shape up to 512 cells on the general path), stride = 3 ints (x,y,z),
     voxel_size = 1 float; returns [B,N,Cout].  Differentiable w.r.t. input and kernel only
-    (pointcnn2_acsd.py:31).  ``plan`` optionally reuses a NeighborPlan built for the same points,
+    (pointcnn2_acsd.py:31).  float32 tensors, or float64 throughout (the reference's T = double registration,
+    register_op.cpp:45: predicate and sums in double, general path).  ``plan`` optionally reuses a NeighborPlan built
+    for the same points,
     stride and voxel size (e.g. across layers).  ``activation="selu"`` returns ``selu(conv3p(...))`` with the
     activation fused into the kernel's epilogue (and its derivative applied to the incoming gradient in backward).
     """
