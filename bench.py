@@ -442,14 +442,18 @@ def timed(fn, steps, world, device, finish=None):
     import torch.distributed as dist
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]     # one record per step: median and best
     e0.record()
-    for _ in range(steps):
+    for i in range(steps):
         fn()
+        marks[i].record()
     if finish:
         finish()
     e1.record()
     barrier(world)
     ms = e0.elapsed_time(e1)
+    per = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+    timed.last = {"median_ms": float(np.median(per)), "best_ms": float(min(per)), "worst_ms": float(max(per))}
     if world > 1:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -591,9 +595,33 @@ def gpu_arm(args):
     # the reported step time is taken WITHOUT the per-kernel event pairs (two cudaEventRecord per launch open small gaps
     # between dependent kernels); the per-kernel breakdown comes from a second, instrumented pass over the same steps
     ms_step = timed(run.step, args.steps, world, device, finish=run.join)
+    step_spread = dict(timed.last)
     clocks = sampler.stop() if rank == 0 else None
     ms_profiled, launches, kern = profile_kernels(L, run.step, args.steps, world, device, finish=run.join)
     value = run.B_global * N / (ms_step * 1e-3)
+
+    # ---- forward-only and backward-only, this rank's shard, no collective ---------------------------
+    from pointwise_b200 import NeighborPlan, conv3p_backward, conv3p_forward
+    d_ = run.devt
+
+    def fwd_only():
+        return conv3p_forward(NeighborPlan(d_["points"], run.stride, VOXEL, check=False, capacity=run.capacity),
+                              d_["input"], d_["filter"])
+
+    held = NeighborPlan(d_["points"], run.stride, VOXEL, check=False, capacity=run.capacity)
+
+    def bwd_only():          # plan reused from forward; backward lists rebuilt every time (they are per step)
+        held.has_backward = False
+        return conv3p_backward(held, d_["grad_out"], d_["input"], d_["filter"])
+
+    phases = {}
+    for name, fn, what in (("forward", fwd_only, "plan build (sort + search) + forward kernel"),
+                           ("backward", bwd_only, "backward lists + both gradient kernels + reduction, plan reused")):
+        for _ in range(3):
+            fn()
+        ms_p = timed(fn, args.steps, 1, device)
+        phases[name] = {"ms": ms_p, "points_per_s_per_gpu": run.pts / (ms_p * 1e-3), "includes": what}
+    del held
 
     # ---- checks on the very batch that was timed (outside the timed regions) ----------------------------------
     plan, y, gi, gf = run.step(collective=False)
@@ -704,6 +732,8 @@ def gpu_arm(args):
                 "api": "pointwise_b200.host_api.HostConv3p (pinned host in/out, copies overlapped with compute)"},
         "gpu_launches": int(launches),
         "ms_per_step_with_kernel_timers": ms_profiled,
+        "step_spread_rank0": step_spread,
+        "phases": phases,
         "roofline": roof,
         "kernels": kernels,
     }
