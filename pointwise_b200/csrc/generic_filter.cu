@@ -17,8 +17,10 @@
 // on the caller's double data.
 //
 // Workspace: [standard plan buffer (sort, lists) | count table [B*N][cells] | forward cell of every pair |
-//             backward cell of every pair | per-cloud grad_filter partials (T) | double only: points as float,
+//             backward cell of every pair | grad_filter partials per (cloud, chunk) (T) | double only: points as float,
 //             per-cloud minimum in double].
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace c3p {
@@ -344,20 +346,22 @@ k_generic_backward_input(GenGeom q, long long pts, long long capacity, int Cin, 
   }
 }
 
-// grad_filter[f', k, c] += g[ii, c] * in[j, k] / count(ii, f')   (:696).  One CTA per cloud walks its points and their
-// backward pairs in order; thread e owns elements e, e + blockDim, ... of the cloud's partial (fixed order of additions).
+// grad_filter[f', k, c] += g[ii, c] * in[j, k] / count(ii, f')   (:696).  CTA (b, s) walks chunk s of cloud b's points and
+// their backward pairs in order; thread e owns elements e, e + blockDim, ... of the CTA's partial (fixed order of
+// additions; the partials are summed in a fixed order afterwards).
 template <typename T>
 __global__ void __launch_bounds__(GEN_THREADS)
-k_generic_backward_filter(GenGeom q, int N, long long capacity, int Cin, int Cout, PlanView v, GenView gv,
+k_generic_backward_filter(GenGeom q, int N, int chunks, long long capacity, int Cin, int Cout, PlanView v, GenView gv,
                           const T* __restrict__ grad_out, const T* __restrict__ input) {
   using A = GenAr<T>;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / chunks, sc = blockIdx.x - b * chunks;
   const int KC = Cin * Cout;
-  T* part = static_cast<T*>(gv.partial) + (size_t)b * q.cells * KC;
+  T* part = static_cast<T*>(gv.partial) + (size_t)blockIdx.x * q.cells * KC;
   const int* members_of = reinterpret_cast<const int*>(v.bwd_weight);
   for (int e = threadIdx.x; e < q.cells * KC; e += GEN_THREADS) part[e] = (T)0;
   __syncthreads();
-  for (int jj = 0; jj < N; ++jj) {
+  const int j_lo = (int)((long long)N * sc / chunks), j_hi = (int)((long long)N * (sc + 1) / chunks);
+  for (int jj = j_lo; jj < j_hi; ++jj) {
     const size_t j = (size_t)b * N + jj;
     const long long begin = v.pair_begin[j];
     if (begin + v.pair_len[j] > capacity) continue;
@@ -392,10 +396,22 @@ bool generic_filter_supported(const int dims_zyx[3]) {
   return (long long)dims_zyx[0] * dims_zyx[1] * dims_zyx[2] <= GEN_MAX_CELLS;
 }
 
+// Chunks per cloud of the weight-gradient kernel: about two CTAs per SM in total, at least 32 points per chunk, and at
+// most 512 MB of partials.
+static int gen_chunks(const conv3p_geom_t* g, int cells, int Cin, int Cout, size_t elem) {
+  if (g->B <= 0 || g->N <= 0) return 1;
+  long long s = (2LL * sm_count() + g->B - 1) / g->B;
+  s = std::min<long long>(s, std::max(1, g->N / 32));
+  const size_t one = elem * (size_t)g->B * cells * Cin * Cout;
+  if (one > 0) s = std::min<long long>(s, (long long)((512ull << 20) / one));
+  return (int)std::max<long long>(1, s);
+}
+
 static size_t gen_extra_bytes(const conv3p_geom_t* g, int cells, int Cin, int Cout, size_t elem) {
   const size_t pts = (size_t)g->B * g->N, cap = (size_t)g->pair_capacity;
+  const size_t parts = (size_t)g->B * gen_chunks(g, cells, Cin, Cout, elem);
   size_t n = align_up(sizeof(int) * pts * cells) + 2 * align_up(sizeof(int) * cap) +
-             align_up(elem * (size_t)g->B * cells * Cin * Cout) + 256;
+             align_up(elem * parts * cells * Cin * Cout) + 256;
   if (elem == 8) n += align_up(sizeof(float) * pts * 3) + align_up(sizeof(double) * (size_t)g->B * 3);
   return n;
 }
@@ -414,7 +430,7 @@ static GenView carve_gen(const conv3p_geom_t* g, int cells, int Cin, int Cout, v
   gv.count = reinterpret_cast<int*>(p); p += align_up(sizeof(int) * pts * cells);
   gv.pair_f = reinterpret_cast<int*>(p); p += align_up(sizeof(int) * cap);
   gv.bwd_f = reinterpret_cast<int*>(p); p += align_up(sizeof(int) * cap);
-  gv.partial = p; p += align_up(elem * (size_t)g->B * cells * Cin * Cout);
+  gv.partial = p; p += align_up(elem * (size_t)g->B * gen_chunks(g, cells, Cin, Cout, elem) * cells * Cin * Cout);
   gv.points_f32 = nullptr;
   gv.dmin = nullptr;
   if (elem == 8) {
@@ -507,20 +523,22 @@ static int generic_backward_t(const conv3p_geom_t* g, const int dims_zyx[3], dou
   }
   C3P_LAUNCH_CHECK("k_generic_backward_input");
   if (grad_filter) {
+    const int chunks = gen_chunks(g, q.cells, Cin, Cout, sizeof(T));
     {
       LaunchTimer timer_("k_generic_backward_filter", stream);
-      k_generic_backward_filter<T><<<g->B, GEN_THREADS, 0, stream>>>(q, g->N, g->pair_capacity, Cin, Cout, v, gv, grad_out, input);
+      k_generic_backward_filter<T><<<g->B * chunks, GEN_THREADS, 0, stream>>>(q, g->N, chunks, g->pair_capacity, Cin, Cout,
+                                                                               v, gv, grad_out, input);
     }
     C3P_LAUNCH_CHECK("k_generic_backward_filter");
     if (sizeof(T) == 8) {
       {
         LaunchTimer timer_("k_reduce_partials", stream);
         k_generic_reduce_f64<<<(unsigned)((nW + 255) / 256), 256, 0, stream>>>(
-            static_cast<const double*>(gv.partial), g->B, nW, reinterpret_cast<double*>(grad_filter), v.header);
+            static_cast<const double*>(gv.partial), g->B * chunks, nW, reinterpret_cast<double*>(grad_filter), v.header);
       }
       C3P_LAUNCH_CHECK("k_reduce_partials");
     } else {
-      st = launch_reduce_partials(static_cast<const float*>(gv.partial), g->B, nW, reinterpret_cast<float*>(grad_filter),
+      st = launch_reduce_partials(static_cast<const float*>(gv.partial), g->B * chunks, nW, reinterpret_cast<float*>(grad_filter),
                                   v.header, stream);
       if (st) return st;
     }
