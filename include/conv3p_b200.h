@@ -245,7 +245,7 @@ long long conv3p_launch_count(int reset);
  * ablation flags for A/B timing (tools/engine_timing.py, tools/ab_backward.py): 32 = phase timers of the gather+MMA
  * kernel, 256 = no G store shared between the two gradient kernels, 512 = three TF32 products (3xTF32) instead of
  * one TF32 product + BF16 correction products in the tensor-core kernels, 1024 = first version of the small-channel
- * kernels.  Returns the previous value.  Process-wide (a test/benchmark knob, not part of the operator's state). */
+ * kernels, 2048 = no channel padding onto the tensor-core kernels (36->13 and the like stay on the fp32 engines).  Returns the previous value.  Process-wide (a test/benchmark knob, not part of the operator's state). */
 int conv3p_set_engine(int engine);
 
 /* Profiling helpers of tools/engine_timing.py: read and clear the device-side cycle counters the gather+MMA kernel

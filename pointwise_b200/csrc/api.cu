@@ -1,4 +1,5 @@
 // api.cu -- the C ABI of libconv3p_b200.so (declared in include/conv3p_b200.h).
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -383,7 +384,7 @@ int conv3p_plan_publish_stats(const conv3p_geom_t* geom, const void* plan, long 
   return CONV3P_OK;
 }
 
-size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
+static size_t scratch_bytes_plain(const conv3p_geom_t* geom, int Cin, int Cout) {
   if (check_geom(geom) || check_channels(Cin, Cout)) return 0;
   // [weight panel images | work-item lists of the tensor-core gather kernels | split-K partials of grad_filter]
   size_t filt = backward_filter_scratch_bytes(geom, Cin, Cout);
@@ -398,10 +399,141 @@ size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
   return weight_panel_bytes(Cin, Cout) + tc_items_bytes(geom, Cin, Cout) + align_up(filt) + 256;
 }
 
+// ---- channel padding: shapes the tensor-core kernels do not take as they are (36->13 of the segmentation network,
+// 48 or 100 channels, ...) run on them with the channels zero-padded -- Cin to a multiple of 32, Cout to a multiple of 16
+// (forward) or to 32 / 64 / 128 / 256 (backward) -- in copies held in the scratch buffer: padded input rows and
+// weights contribute exact zeros, padded outputs are dropped.  Not for the tiny shapes (both counts <= 16: the
+// warp-per-point kernels win there) and not when the padded product is more than 6x the real one.  Engine flag 2048
+// switches it off (A/B timing).
+static bool pad_channels(const conv3p_geom_t* g, int Cin, int Cout, bool backward, int* Pi, int* Po) {
+  if (!engine_allows_tc() || engine_flag(2048)) return false;
+  if (Cin > 256 || Cout > 256 || (Cin <= 16 && Cout <= 16)) return false;
+  const int pi = (Cin + 31) / 32 * 32;
+  const int po = !backward ? (Cout + 15) / 16 * 16 : Cout <= 32 ? 32 : Cout <= 64 ? 64 : Cout <= 128 ? 128 : 256;
+  if (pi == Cin && po == Cout) return false;
+  if ((long long)pi * po > 6LL * Cin * Cout) return false;
+  if (!backward) {
+    if (Cin % 4 == 0 && Cout % 4 == 0 && forward_tc_supported(g->N, g->pair_capacity, Cin, Cout)) return false;
+    if (!forward_tc_supported(g->N, g->pair_capacity, pi, po)) return false;
+  } else {
+    if (Cin % 4 == 0 && Cout % 4 == 0 && backward_input_tc_supported(g->N, g->pair_capacity, Cin, Cout) &&
+        backward_filter2_supported(g->N, g->pair_capacity, Cin, Cout))
+      return false;
+    if (!backward_input_tc_supported(g->N, g->pair_capacity, pi, po) ||
+        !backward_filter2_supported(g->N, g->pair_capacity, pi, po))
+      return false;
+  }
+  *Pi = pi;
+  *Po = po;
+  return true;
+}
+
+struct PadLayout {     // byte offsets into the scratch buffer
+  size_t a, b, c, w, gf, inner, total;
+};
+// forward: [x_pad | y_pad | W_pad | inner scratch]; backward: [g_pad | x_pad | gi_pad | W_pad | gf_pad | inner (+ G store)]
+static PadLayout pad_layout(const conv3p_geom_t* g, int Pi, int Po, bool backward, bool with_g_store) {
+  const size_t pts = (size_t)g->B * g->N;
+  PadLayout L{};
+  size_t o = 0;
+  if (!backward) {
+    L.a = o; o += align_up(pts * Pi * sizeof(float));
+    L.b = o; o += align_up(pts * Po * sizeof(float));
+    L.c = 0;
+    L.w = o; o += align_up((size_t)C3P_NCELL * Pi * Po * sizeof(float));
+    L.gf = 0;
+  } else {
+    L.a = o; o += align_up(pts * Po * sizeof(float));
+    L.b = o; o += align_up(pts * Pi * sizeof(float));
+    L.c = o; o += align_up(pts * Pi * sizeof(float));
+    L.w = o; o += align_up((size_t)C3P_NCELL * Pi * Po * sizeof(float));
+    L.gf = o; o += align_up((size_t)C3P_NCELL * Pi * Po * sizeof(float));
+  }
+  L.inner = o;
+  o += scratch_bytes_plain(g, Pi, Po);
+  if (backward && with_g_store) o += g_store_bytes(g, Pi, Po);
+  L.total = o;
+  return L;
+}
+
+size_t conv3p_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
+  size_t n = scratch_bytes_plain(geom, Cin, Cout);
+  if (!n) return 0;
+  int pi, po;
+  if (pad_channels(geom, Cin, Cout, false, &pi, &po)) n = std::max(n, pad_layout(geom, pi, po, false, false).total);
+  if (pad_channels(geom, Cin, Cout, true, &pi, &po)) n = std::max(n, pad_layout(geom, pi, po, true, false).total);
+  return n;
+}
+
 size_t conv3p_backward_scratch_bytes(const conv3p_geom_t* geom, int Cin, int Cout) {
   const size_t base = conv3p_scratch_bytes(geom, Cin, Cout);
   if (!base) return 0;
-  return base + g_store_bytes(geom, Cin, Cout);
+  size_t n = std::max(base, scratch_bytes_plain(geom, Cin, Cout) + g_store_bytes(geom, Cin, Cout));
+  int pi, po;
+  if (pad_channels(geom, Cin, Cout, true, &pi, &po)) n = std::max(n, pad_layout(geom, pi, po, true, true).total);
+  return n;
+}
+
+// rows [pts][C] (row stride ls) -> [pts][P] with zeros in the padding, and back (row stride lo)
+__global__ void k_pad_channels(const float* __restrict__ src, long long ls, int C, float* __restrict__ dst, int P,
+                               long long pts) {
+  const long long total = pts * P;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / P;
+    const int c = (int)(e - r * P);
+    dst[e] = c < C ? src[r * ls + c] : 0.f;
+  }
+}
+__global__ void k_unpad_channels(const float* __restrict__ src, int P, float* __restrict__ dst, long long lo, int C,
+                                 long long pts) {
+  const long long total = pts * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / C;
+    const int c = (int)(e - r * C);
+    dst[r * lo + c] = src[r * P + c];
+  }
+}
+// filter [27][Cin][Cout] <-> [27][Pi][Po]
+__global__ void k_pad_filter(const float* __restrict__ src, int Cin, int Cout, float* __restrict__ dst, int Pi, int Po,
+                             int to_padded) {
+  const int total = C3P_NCELL * (to_padded ? Pi * Po : Cin * Cout);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    if (to_padded) {
+      const int c = e % Po, k = (e / Po) % Pi, f = e / (Po * Pi);
+      dst[e] = (k < Cin && c < Cout) ? src[((size_t)f * Cin + k) * Cout + c] : 0.f;
+    } else {
+      const int c = e % Cout, k = (e / Cout) % Cin, f = e / (Cout * Cin);
+      dst[e] = src[((size_t)f * Pi + k) * Po + c];
+    }
+  }
+}
+static int launch_pad(const float* src, long long ls, int C, float* dst, int P, long long pts, cudaStream_t stream) {
+  {
+    LaunchTimer timer_("k_pad_channels", stream);
+    const long long blocks = std::min<long long>((pts * P + 255) / 256, (long long)sm_count() * 16);
+    k_pad_channels<<<(unsigned)blocks, 256, 0, stream>>>(src, ls, C, dst, P, pts);
+  }
+  C3P_LAUNCH_CHECK("k_pad_channels");
+  return CONV3P_OK;
+}
+static int launch_unpad(const float* src, int P, float* dst, long long lo, int C, long long pts, cudaStream_t stream) {
+  {
+    LaunchTimer timer_("k_unpad_channels", stream);
+    const long long blocks = std::min<long long>((pts * C + 255) / 256, (long long)sm_count() * 16);
+    k_unpad_channels<<<(unsigned)blocks, 256, 0, stream>>>(src, P, dst, lo, C, pts);
+  }
+  C3P_LAUNCH_CHECK("k_unpad_channels");
+  return CONV3P_OK;
+}
+static int launch_pad_filter(const float* src, int Cin, int Cout, float* dst, int Pi, int Po, bool to_padded,
+                             cudaStream_t stream) {
+  {
+    LaunchTimer timer_("k_pad_filter", stream);
+    const int total = C3P_NCELL * (to_padded ? Pi * Po : Cin * Cout);
+    k_pad_filter<<<(total + 255) / 256, 256, 0, stream>>>(src, Cin, Cout, dst, Pi, Po, to_padded ? 1 : 0);
+  }
+  C3P_LAUNCH_CHECK("k_pad_filter");
+  return CONV3P_OK;
 }
 
 int conv3p_forward_ex_f32(const conv3p_geom_t* geom, const void* plan, const float* input,
@@ -423,6 +555,25 @@ int conv3p_forward_ex_f32(const conv3p_geom_t* geom, const void* plan, const flo
   io.out_stride = output_row_stride == Cout ? 0 : output_row_stride;
   io.activation = activation;
   const long long ls = io.src_stride ? io.src_stride : Cin, lo = io.out_stride ? io.out_stride : Cout;
+  {
+    int pi, po;
+    if (pad_channels(geom, Cin, Cout, false, &pi, &po)) {
+      const PadLayout P = pad_layout(geom, pi, po, false, false);
+      if (scratch && scratch_bytes >= P.total) {     // (a smaller scratch buffer: the fp32 engines below)
+        char* sp = static_cast<char*>(scratch);
+        float* x_pad = reinterpret_cast<float*>(sp + P.a);
+        float* y_pad = reinterpret_cast<float*>(sp + P.b);
+        float* w_pad = reinterpret_cast<float*>(sp + P.w);
+        const long long pts = (long long)geom->B * geom->N;
+        if ((st = launch_pad(input, ls, Cin, x_pad, pi, pts, stream))) return st;
+        if ((st = launch_pad_filter(filter, Cin, Cout, w_pad, pi, po, true, stream))) return st;
+        st = conv3p_forward_ex_f32(geom, plan, x_pad, 0, w_pad, pi, po, y_pad, 0, activation, sp + P.inner,
+                                   scratch_bytes - P.inner, stream);
+        if (st) return st;
+        return launch_unpad(y_pad, po, output, lo, Cout, pts, stream);
+      }
+    }
+  }
   const bool rows_aligned = ls % 4 == 0 && lo % 4 == 0 && reinterpret_cast<uintptr_t>(input) % 16 == 0 &&
                             reinterpret_cast<uintptr_t>(output) % 16 == 0;
   // tensor cores need 16-byte aligned rows; other layouts fall back to the fp32 engines
@@ -475,6 +626,34 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
     if (grad_filter) C3P_CUDA(cudaMemsetAsync(grad_filter, 0, sizeof(float) * C3P_NCELL * (size_t)Cin * Cout, stream));
     return CONV3P_OK;
   }
+  {
+    int pi, po;
+    if (pad_channels(geom, Cin, Cout, true, &pi, &po)) {
+      const bool share = grad_input && grad_filter && !engine_flag(256);
+      PadLayout P = pad_layout(geom, pi, po, true, share);
+      if (share && !(scratch && scratch_bytes >= P.total)) P = pad_layout(geom, pi, po, true, false);
+      if (scratch && scratch_bytes >= P.total) {     // (a smaller scratch buffer: the fp32 engines below)
+        char* sp = static_cast<char*>(scratch);
+        float* g_pad = reinterpret_cast<float*>(sp + P.a);
+        float* x_pad = reinterpret_cast<float*>(sp + P.b);
+        float* gi_pad = reinterpret_cast<float*>(sp + P.c);
+        float* w_pad = reinterpret_cast<float*>(sp + P.w);
+        float* gf_pad = reinterpret_cast<float*>(sp + P.gf);
+        const long long pts = (long long)geom->B * geom->N;
+        if (grad_input && !filter) return CONV3P_ERR_INVALID_ARGUMENT;
+        if (grad_filter && !input) return CONV3P_ERR_INVALID_ARGUMENT;
+        if ((st = launch_pad(grad_output, Cout, Cout, g_pad, po, pts, stream))) return st;
+        if (grad_filter && (st = launch_pad(input, Cin, Cin, x_pad, pi, pts, stream))) return st;
+        if (grad_input && (st = launch_pad_filter(filter, Cin, Cout, w_pad, pi, po, true, stream))) return st;
+        st = conv3p_backward_f32(geom, plan, g_pad, x_pad, w_pad, pi, po, grad_input ? gi_pad : nullptr,
+                                 grad_filter ? gf_pad : nullptr, sp + P.inner, scratch_bytes - P.inner, stream);
+        if (st) return st;
+        if (grad_input && (st = launch_unpad(gi_pad, pi, grad_input, Cin, Cin, pts, stream))) return st;
+        if (grad_filter && (st = launch_pad_filter(gf_pad, Cin, Cout, grad_filter, pi, po, false, stream))) return st;
+        return CONV3P_OK;
+      }
+    }
+  }
   // Engine per gradient.  The tensor-core kernels use 16-byte vector accesses; other layouts run on the fp32 engines.
   const bool aligned = reinterpret_cast<uintptr_t>(grad_output) % 16 == 0 && Cin % 4 == 0 && Cout % 4 == 0 &&
                        reinterpret_cast<uintptr_t>(grad_input) % 16 == 0 && reinterpret_cast<uintptr_t>(input) % 16 == 0;
@@ -488,7 +667,7 @@ int conv3p_backward_f32(const conv3p_geom_t* geom, const void* plan, const float
   float* g_store = nullptr;
   if (gi_tc && gf_tc && !engine_flag(256)) {
     const size_t gsb = g_store_bytes(geom, Cin, Cout);
-    const size_t base = conv3p_scratch_bytes(geom, Cin, Cout);
+    const size_t base = scratch_bytes_plain(geom, Cin, Cout);
     if (gsb && scratch && scratch_bytes >= base + gsb) g_store = reinterpret_cast<float*>(static_cast<char*>(scratch) + base);
   }
   // scratch layout: [weight panel images | 128-row work-item lists | grad_filter scratch (its 64-row lists first)]

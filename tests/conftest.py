@@ -39,3 +39,15 @@ def port():
     import oracle
     oracle.build()
     return oracle.port()
+
+
+@pytest.fixture(autouse=True)
+def fresh_capacity_estimates(request):
+    """Every GPU test starts without learned pair-capacity estimates: they are keyed by (B, N, stride, voxel) only, so
+    a test that reuses a shape with denser clouds would otherwise trip the deferred overflow check of NeighborPlan
+    (documented behaviour: poison + Conv3pError + raised estimate) depending on the order the tests run in."""
+    if "gpu" in request.keywords:
+        from pointwise_b200 import ops
+        ops._capacity_hint.clear()
+        ops._generic_capacity_hint.clear()
+    yield

@@ -450,12 +450,49 @@ def test_tensor_core_engine_matches_oracle_and_simt(port, Cin, Cout):
         assert assert_close_scaled(gfs[eng], r[4], r[5], RTOL, ATOL, f"grad_filter[{eng}]") < RTOL
     assert not np.array_equal(outs["simt"], outs["tc"]), "tensor-core engine was not selected (forward)"
     assert not np.array_equal(outs["tile"], outs["tc"]), "engine 'tile' must not use tensor cores"
-    if Cout % 32 == 0:
-        assert not np.array_equal(gins["simt"], gins["tc"]), "tensor-core engine was not selected (grad_input)"
-    if tc_filter_shape(Cin, Cout):
-        assert not np.array_equal(gfs["simt"], gfs["tc"]), "tensor-core engine was not selected (grad_filter)"
-    else:
-        assert np.array_equal(gfs["simt"], gfs["tc"])
+    # (96, 48) reaches the gradient kernels through channel padding (Cout -> 64), the others as they are
+    assert not np.array_equal(gins["simt"], gins["tc"]), "tensor-core engine was not selected (grad_input)"
+    assert not np.array_equal(gfs["simt"], gfs["tc"]), "tensor-core engine was not selected (grad_filter)"
+
+
+# Shapes the tensor-core kernels do not take as they are: zero-padded channels (api.cu, pad_channels).  36 -> 13 is the
+# segmentation network's last layer (scene_seg/pointcnn_scene_seg_acsd.py:56-57).
+# (Cin, Cout, forward padded, backward padded): 64 -> 48 is a tensor-core forward shape as it is; 33 -> 8 pads to
+# 64 x 16 forward but would need 64 x 32 backward, more than 6x the real product.
+PADDED_SHAPES = [(36, 13, True, True), (40, 24, True, True), (20, 70, True, True), (64, 48, False, True),
+                 (100, 100, True, True), (17, 33, True, True), (33, 8, True, False)]
+
+
+@pytest.mark.parametrize("Cin,Cout,fwd_padded,bwd_padded", PADDED_SHAPES)
+def test_channel_padding_onto_tensor_cores_matches_oracle(port, Cin, Cout, fwd_padded, bwd_padded):
+    """Padded shapes stay inside the operator's tolerance, really take the tensor-core kernels (results differ from
+    the fp32 engines', which engine flag 2048 selects), and the padding leaks nothing into the results."""
+    from pointwise_b200 import NeighborPlan, _lib, conv3p_backward, conv3p_forward
+    B, N, stride = 2, 1100, (1, 2, 1)
+    pr = make_problem(B, N, Cin, Cout, "room", seed=21)
+    plan = NeighborPlan(dev(pr["points"]), stride, V)
+    o32, o64, oabs = port.forward(pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
+    r = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, V, with64=True)
+    L = _lib.lib()
+    res = {}
+    for flags in (0, 2048):
+        prev = L.conv3p_set_engine(flags)
+        try:
+            y = conv3p_forward(plan, dev(pr["input"]), dev(pr["filter"]))
+            gi, gf = conv3p_backward(plan, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]))
+            gi_only, none = conv3p_backward(plan, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]),
+                                            need_filter_grad=False)
+            res[flags] = (y.cpu().numpy(), gi.cpu().numpy(), gf.cpu().numpy())
+            assert none is None and torch.equal(gi_only, gi)
+        finally:
+            L.conv3p_set_engine(prev)
+        assert assert_close_scaled(res[flags][0], o64, oabs, RTOL, ATOL, f"forward[{flags}]") < RTOL
+        assert assert_close_scaled(res[flags][1], r[2], r[3], RTOL, ATOL, f"grad_input[{flags}]") < RTOL
+        assert assert_close_scaled(res[flags][2], r[4], r[5], RTOL, ATOL, f"grad_filter[{flags}]") < RTOL
+    for a, b, what, padded in zip(res[0], res[2048], ("forward", "grad_input", "grad_filter"),
+                                  (fwd_padded, bwd_padded, bwd_padded)):
+        assert a.shape == b.shape
+        assert np.array_equal(a, b) != padded, f"{what}: padded tensor-core path expected = {padded}"
 
 
 def test_host_pipeline_matches_direct_calls():
