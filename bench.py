@@ -780,7 +780,8 @@ def run_sweep(L, device, warm=2, steps=5):
         fwd = next((k for k in ("k_forward_tc", "k_small_forward", "k_gather_contract_fwd") if k in kern), None)
         row = {"points_per_s": r.B * r.N / (ms * 1e-3), "ms_per_step": round(ms, 4), "clouds": r.B, "N": r.N,
                "C": r.Cin, "kbar": round(r.kbar, 2), "nbins": round(r.nbins, 2),
-               "engine": "tcgen05 3xTF32" if "k_forward_tc" in kern else
+               "engine": ("tcgen05 TF32 + BF16 corrections" + (", channels zero-padded" if "k_pad_channels" in kern else ""))
+                         if "k_forward_tc" in kern else
                          ("fp32 warp-per-point" if "k_small_forward" in kern else "fp32 tile"),
                "kernels_ms": {k: round(v[1] / v[0], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])[:6]}}
         if fwd:

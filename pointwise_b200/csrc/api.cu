@@ -402,16 +402,27 @@ static size_t scratch_bytes_plain(const conv3p_geom_t* geom, int Cin, int Cout) 
 // ---- channel padding: shapes the tensor-core kernels do not take as they are (36->13 of the segmentation network,
 // 48 or 100 channels, ...) run on them with the channels zero-padded -- Cin to a multiple of 32, Cout to a multiple of 16
 // (forward) or to 32 / 64 / 128 / 256 (backward) -- in copies held in the scratch buffer: padded input rows and
-// weights contribute exact zeros, padded outputs are dropped.  Not for the tiny shapes (both counts <= 16: the
-// warp-per-point kernels win there) and not when the padded product is more than 6x the real one.  Engine flag 2048
-// switches it off (A/B timing).
+// weights contribute exact zeros, padded outputs are dropped.  Not when the padded product is more than 6x the real
+// one; the tiny shapes (both counts <= 16) only for large batches, see below.  Engine flag 2048 switches it off (A/B
+// timing).
 static bool pad_channels(const conv3p_geom_t* g, int Cin, int Cout, bool backward, int* Pi, int* Po) {
   if (!engine_allows_tc() || engine_flag(2048)) return false;
-  if (Cin > 256 || Cout > 256 || (Cin <= 16 && Cout <= 16)) return false;
+  // Tiny shapes (both counts <= 16, the 9 -> 9 layers of both networks): measured on one B200, fwd+bwd step of one 9 -> 9
+  // layer on the warp-per-point kernels against padded to 32 x 16 / 32 x 32 -- 262,144 points 2.95 -> 2.19 ms (4096 per
+  // cloud), 6.34 -> 4.62 ms (16384 per cloud), 1.91 -> 1.75 ms (1024 per cloud); 65,536 points 0.794 -> 0.717 ms, but
+  // nine more launches per layer, which a whole network at that size pays for on the host (segmentation network 4.69
+  // -> 4.97 ms); 32,768 points 0.324 -> 0.407 ms.  So only from 128k points up (CONV3P_PAD_TINY_MIN_POINTS).
+  static const long long tiny_min_points = [] {
+    const char* e = getenv("CONV3P_PAD_TINY_MIN_POINTS");
+    return e ? atoll(e) : 131072LL;
+  }();
+  if (Cin > 256 || Cout > 256) return false;
+  const bool tiny = Cin <= 16 && Cout <= 16;
+  if (tiny && (long long)g->B * g->N < tiny_min_points) return false;
   const int pi = (Cin + 31) / 32 * 32;
   const int po = !backward ? (Cout + 15) / 16 * 16 : Cout <= 32 ? 32 : Cout <= 64 ? 64 : Cout <= 128 ? 128 : 256;
   if (pi == Cin && po == Cout) return false;
-  if ((long long)pi * po > 6LL * Cin * Cout) return false;
+  if (!tiny && (long long)pi * po > 6LL * Cin * Cout) return false;
   if (!backward) {
     if (Cin % 4 == 0 && Cout % 4 == 0 && forward_tc_supported(g->N, g->pair_capacity, Cin, Cout)) return false;
     if (!forward_tc_supported(g->N, g->pair_capacity, pi, po)) return false;
