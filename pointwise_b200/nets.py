@@ -29,6 +29,10 @@ from .ops import NeighborPlan, conv3p, conv3p_forward, parse_stride, parse_voxel
 # False: every conv3p call builds its own plan (what a literal drop-in call without `plan=` does) -- bench.py's A/B of
 # plan sharing.  Results are identical either way.
 SHARE_PLANS = True
+# Passed to NeighborPlan(check=...): True = learned capacity with the deferred overflow check (the default); False =
+# learned capacity, poison only, nothing read back -- what a CUDA-graph capture of a training step needs (no host
+# polling inside the captured region; tools/graph_net.py).
+PLAN_CHECK = True
 
 
 class PlanCache:
@@ -42,9 +46,9 @@ class PlanCache:
     def get(self, stride) -> NeighborPlan:
         s = parse_stride(stride)
         if not SHARE_PLANS:
-            return NeighborPlan(self.points, s, self.voxel)
+            return NeighborPlan(self.points, s, self.voxel, check=PLAN_CHECK)
         if s not in self.plans:
-            self.plans[s] = NeighborPlan(self.points, s, self.voxel)
+            self.plans[s] = NeighborPlan(self.points, s, self.voxel, check=PLAN_CHECK)
         return self.plans[s]
 
 
