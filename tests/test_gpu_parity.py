@@ -707,3 +707,34 @@ def test_whole_step_is_cuda_graph_capturable():
     graph.replay()
     torch.cuda.synchronize()
     assert all(torch.equal(a, b) for a, b in zip(want, got))
+
+
+def test_channel_padding_with_strided_rows_selu_and_overflow_poison():
+    """The padded tensor-core path behind conv3p_forward_ex_f32: input and output as channel slices of wider buffers,
+    SELU in the epilogue, and NaN poisoning when the plan's lists overflowed -- same results as the fp32 engines
+    (engine flag 2048) up to the operator's tolerance, untouched channels outside the slices."""
+    from pointwise_b200 import NeighborPlan, _lib, conv3p_backward, conv3p_forward
+    B, N, Cin, Cout = 2, 700, 36, 13
+    pr = make_problem(B, N, Cin, Cout, "room", seed=33)
+    plan = NeighborPlan(dev(pr["points"]), (1, 1, 1), V)
+    wide_in = torch.full((B, N, 50), 7.0, device="cuda")
+    wide_in[..., 5:5 + Cin] = dev(pr["input"])
+    L = _lib.lib()
+    outs = {}
+    for flags in (0, 2048):
+        prev = L.conv3p_set_engine(flags)
+        try:
+            wide_out = torch.full((B, N, 20), -3.0, device="cuda")
+            conv3p_forward(plan, wide_in[..., 5:5 + Cin], dev(pr["filter"]), activation="selu", out=wide_out[..., 2:2 + Cout])
+            outs[flags] = wide_out.cpu().numpy()
+        finally:
+            L.conv3p_set_engine(prev)
+        assert (outs[flags][..., :2] == -3.0).all() and (outs[flags][..., 2 + Cout:] == -3.0).all()
+    assert not np.array_equal(outs[0], outs[2048])
+    np.testing.assert_allclose(outs[0], outs[2048], rtol=2e-4, atol=2e-5)
+    # overflow: a plan built with too small a capacity poisons the padded path's outputs too
+    small = NeighborPlan(dev(pr["points"]), (1, 1, 1), V, capacity=2000, check=False)
+    y = conv3p_forward(small, dev(pr["input"]), dev(pr["filter"]))
+    gi, gf = conv3p_backward(small, dev(pr["grad_out"]), dev(pr["input"]), dev(pr["filter"]))
+    assert torch.isnan(y).any() and torch.isnan(gi).any() and torch.isnan(gf).all()
+    assert not torch.isnan(y).all()          # rows whose lists fit are computed
