@@ -36,7 +36,7 @@ for eng in flags:
     L.conv3p_profile_read(buf, 8192)
     L.conv3p_profile_enable(0)
     print(f"engine flags {eng}:", "  ".join(f"{ln.split()[0]} {float(ln.split()[2]) / int(ln.split()[1]):.4f}"
-                                            for ln in buf.value.decode().splitlines() if "_tc" in ln))
+                                            for ln in buf.value.decode().splitlines() if "_tc" in ln or "group_items" in ln))
     L.conv3p_debug_w2_cycles(buf8)
     if any(buf8):
         sms = torch.cuda.get_device_properties(0).multi_processor_count
