@@ -131,6 +131,7 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
 # neighbour plan
 # --------------------------------------------------------------------------------------------------
 _capacity_hint: dict = {}
+HEADROOM = float(os.environ.get("CONV3P_CAPACITY_HEADROOM", "2.0"))   # learned pair capacity = pairs seen x this
 _pending_checks: list = []     # plans whose deferred overflow check has not been read yet (weak references)
 
 
@@ -197,7 +198,9 @@ class NeighborPlan:
     forward/backward"; the reference's GPU op blocks twice per call, tf_conv3p_atrous.cu:577, 586):
 
     * the first plan of a (B, N, stride, voxel) shape is built with a synchronous check (one 128-byte read-back,
-      rebuilt larger if the guess was too small) and leaves a grow-only estimate with 25 % head-room;
+      rebuilt larger if the guess was too small) and leaves a grow-only estimate with 100 % head-room (``HEADROOM``:
+      the lists cost 12 bytes per pair of CAPACITY in the plan buffer and nothing at run time -- the kernels only touch
+      what is filled -- so the estimate is generous: real scans vary far more from batch to batch than synthetic ones);
     * every later plan of that shape uses the estimate and only ENQUEUES a copy of the plan's counters into pinned
       host memory.  They are looked at later, without waiting -- when the backward pass starts, when the next plan
       is built -- or on ``verify()`` / ``stats``.  Should a batch ever exceed the estimate,
@@ -264,7 +267,7 @@ class NeighborPlan:
 
     def _learn(self, total_pairs: int) -> None:
         """grow-only capacity estimate for the next batch of this shape"""
-        want = int(total_pairs * 1.25) + 1024
+        want = int(total_pairs * HEADROOM) + 1024
         _capacity_hint[self._key] = max(_capacity_hint.get(self._key, 0), want)
 
     # ---- deferred overflow check -----------------------------------------------------------------
