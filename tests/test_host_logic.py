@@ -70,6 +70,34 @@ def test_general_filter_workspace_queries():
     assert L.conv3p_op_workspace_bytes_ex(g, i3(0, 3, 3), 4, 4, 0) == 0
 
 
+def test_double_and_padded_scratch_queries():
+    """Host-side size queries only (no GPU): the double operator's workspace, and the scratch of shapes that run
+    zero-padded on the tensor-core kernels (api.cu, pad_channels) covers the padded copies and the padded shape's own
+    scratch; engine flag 2048 (no padding) gives the smaller figure back."""
+    L = _lib.lib()
+    i3 = C.c_int * 3
+    g = _lib.make_geom(16, 4096, (1, 1, 1), 0.1, 4_000_000)
+    f32 = L.conv3p_op_workspace_bytes_ex(g, i3(3, 3, 3), 9, 9, 1)
+    f64 = L.conv3p_op_workspace_bytes_f64(g, i3(3, 3, 3), 9, 9)
+    assert f64 > 0 and f32 > 0
+    assert L.conv3p_op_workspace_bytes_f64(g, i3(9, 9, 9), 9, 9) == 0
+    pts = 16 * 4096
+    padded = L.conv3p_scratch_bytes(g, 36, 13)
+    assert padded >= L.conv3p_scratch_bytes(g, 64, 32) + 4 * pts * (32 + 64 + 64)      # g_pad, x_pad, gi_pad + inner
+    assert L.conv3p_backward_scratch_bytes(g, 36, 13) >= padded + 4 * pts * 27 * 32     # + the padded shape's G store
+    big = _lib.make_geom(64, 4096, (1, 1, 1), 0.1, 16_000_000)
+    tiny_small, tiny_big = L.conv3p_scratch_bytes(g, 9, 9), L.conv3p_scratch_bytes(big, 9, 9)
+    prev = L.conv3p_set_engine(2048)
+    try:
+        assert L.conv3p_scratch_bytes(g, 36, 13) < padded
+        # tiny shapes are padded only from 128k points up
+        assert L.conv3p_scratch_bytes(g, 9, 9) == tiny_small
+        assert L.conv3p_scratch_bytes(big, 9, 9) < tiny_big
+    finally:
+        L.conv3p_set_engine(prev)
+    assert tiny_big >= 4 * 64 * 4096 * (32 + 32 + 32)
+
+
 def test_collective_helpers_without_a_process_group():
     import torch
     t = torch.ones(3)
