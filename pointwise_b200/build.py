@@ -47,10 +47,10 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = Non
         objs.append(obj)
     failed = False
     for cmd, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0 or verbose:
             print(" ".join(cmd))
-            print(out)
+            print(log)
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
@@ -59,6 +59,9 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = Non
     if res.returncode != 0:
         print(res.stdout + res.stderr)
         raise RuntimeError("link failed")
+    if out:      # a variant's objects are not reused: keep the tree (and what travels to the GPU box) small
+        import shutil
+        shutil.rmtree(obj_dir, ignore_errors=True)
     return lib_path
 
 
