@@ -16,13 +16,21 @@ from helpers import assert_close_scaled  # noqa: E402
 from pointwise_b200 import NeighborPlan, conv3p_backward, conv3p_forward  # noqa: E402
 from pointwise_b200.synth import make_problem  # noqa: E402
 
-budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
-rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-oracle.build()
-port = oracle.port()
 CH = [1, 3, 4, 8, 9, 13, 16, 17, 20, 24, 32, 33, 36, 40, 48, 64, 70, 96, 100, 128]
-t0, cases, worst = time.time(), 0, 0.0
-while time.time() - t0 < budget:
+
+
+def run(budget: float, seed: int):
+    """-> (cases, worst error / sum|terms|); raises AssertionError on the first case out of tolerance."""
+    rng = np.random.default_rng(seed)
+    oracle.build()
+    port = oracle.port()
+    t0, cases, worst = time.time(), 0, 0.0
+    while time.time() - t0 < budget:
+        cases, worst = cases + 1, max(worst, one_case(rng, port))
+    return cases, worst
+
+
+def one_case(rng, port) -> float:
     B, N = int(rng.integers(1, 5)), int(rng.choice([1, 2, 7, 63, 128, 129, 300, 700, 1500]))
     Cin, Cout = int(rng.choice(CH)), int(rng.choice(CH))
     if Cin * Cout > 64 * 128:
@@ -46,8 +54,12 @@ while time.time() - t0 < budget:
     o32, o64, oabs = port.forward(pr["points"], pr["input"], pr["filter"], stride, voxel, with64=True)
     r = port.backward(pr["grad_out"], pr["points"], pr["input"], pr["filter"], stride, voxel, with64=True)
     tag = f"B{B} N{N} {Cin}->{Cout} s{stride} v{voxel} {dist} q{quant}"
-    worst = max(worst, assert_close_scaled(y, o64, oabs, 1e-5, 1e-7, "forward " + tag),
-                assert_close_scaled(gi.cpu().numpy(), r[2], r[3], 1e-5, 1e-7, "grad_input " + tag),
-                assert_close_scaled(gf.cpu().numpy(), r[4], r[5], 1e-5, 1e-7, "grad_filter " + tag))
-    cases += 1
-print(f"fuzz ok: {cases} random cases in {time.time() - t0:.0f} s, worst error / sum|terms| = {worst:.2e} (bound 1e-5)")
+    return max(assert_close_scaled(y, o64, oabs, 1e-5, 1e-7, "forward " + tag),
+               assert_close_scaled(gi.cpu().numpy(), r[2], r[3], 1e-5, 1e-7, "grad_input " + tag),
+               assert_close_scaled(gf.cpu().numpy(), r[4], r[5], 1e-5, 1e-7, "grad_filter " + tag))
+
+
+if __name__ == "__main__":
+    t_ = time.time()
+    n_, w_ = run(float(sys.argv[1]) if len(sys.argv) > 1 else 120.0, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    print(f"fuzz ok: {n_} random cases in {time.time() - t_:.0f} s, worst error / sum|terms| = {w_:.2e} (bound 1e-5)")
