@@ -433,7 +433,12 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gather_mma2(const G2Args a) {
         // BF16 correction panel [lo (32 ch) | hi (32 ch)] per row
         auto store_row = [&](int p, const float4 (&v)[NKC]) {
           const uint32_t o = panel_chunk_offset(p, l8);
-          if (BF16C) {
+          if (BF16C && !WEIGHTED) {
+            // forward: interleaved correction panel, [lo | hi] of the lane's 4 channels at the hi panel's chunk position
+#pragma unroll
+            for (int kc = 0; kc < NKC; ++kc)
+              g2_store_split16i(stage[kc] + o, stage[kc] + o + 128 * PANEL_ROW_BYTES, v[kc]);
+          } else if (BF16C) {
             // correction panel row = [lo (32 ch) | hi (32 ch)]
             const uint32_t oc = 128 * PANEL_ROW_BYTES + (uint32_t)p * PANEL_ROW_BYTES + ((uint32_t)(l8 & 1) << 3);
             const uint32_t c_lo = oc + ((((uint32_t)l8 >> 1) ^ ((uint32_t)p & 7u)) << 4);

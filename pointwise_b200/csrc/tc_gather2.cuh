@@ -97,6 +97,15 @@ __device__ __forceinline__ void g2_store_split16(uint32_t hi_dst, uint32_t lo16_
   sts64(lo16_dst, pack_bf16x2(l0.x, l0.y), pack_bf16x2(l1.x, l1.y));
   sts64(hi16_dst, pack_bf16x2(h.x, h.y), pack_bf16x2(h.z, h.w));
 }
+// Interleaved K order (tc_common.cuh, panel_offset16i): chunk = [lo (4 bf16) | hi (4 bf16)], one 16-byte store.
+__device__ __forceinline__ void g2_store_split16i(uint32_t hi_dst, uint32_t c_dst, const float4& v) {
+  const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+  const float2 l0 = __fadd2_rn(make_float2(v.x, v.y), make_float2(-h.x, -h.y));
+  const float2 l1 = __fadd2_rn(make_float2(v.z, v.w), make_float2(-h.z, -h.w));
+  sts128(hi_dst, h);
+  sts128(c_dst, make_float4(__uint_as_float(pack_bf16x2(l0.x, l0.y)), __uint_as_float(pack_bf16x2(l1.x, l1.y)),
+                            __uint_as_float(pack_bf16x2(h.x, h.y)), __uint_as_float(pack_bf16x2(h.z, h.w))));
+}
 __device__ __forceinline__ void g2_store_split16(unsigned char* hi_dst, unsigned char* lo16_dst, unsigned char* hi16_dst,
                                                  const float4& v) {
   const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));

@@ -41,7 +41,10 @@ __global__ void k_prep_weight_panels(const float* __restrict__ filter, unsigned 
     unsigned char* base = wp + ((size_t)(f * nkc + kc) * 2) * R * PANEL_ROW_BYTES;
     *reinterpret_cast<float*>(base + panel_offset(r, k)) = h;
     unsigned char* second = base + (size_t)R * PANEL_ROW_BYTES;
-    if (bf16c) {
+    if (bf16c && !transposed_out) {   // forward: interleaved K order (tc_common.cuh, panel_offset16i)
+      *reinterpret_cast<__nv_bfloat16*>(second + panel_offset16i(r, k, 0)) = __float2bfloat16_rn(h);
+      *reinterpret_cast<__nv_bfloat16*>(second + panel_offset16i(r, k, 1)) = __float2bfloat16_rn(w - h);
+    } else if (bf16c) {
       *reinterpret_cast<__nv_bfloat16*>(second + panel_offset16(r, k)) = __float2bfloat16_rn(h);
       *reinterpret_cast<__nv_bfloat16*>(second + panel_offset16(r, 32 + k)) = __float2bfloat16_rn(w - h);
     } else {
