@@ -580,12 +580,14 @@ def gpu_arm(args):
     if args.workload in NETS:
         return net_arm(args, rank, world, device)
     L = _lib.lib()
-    run = Runner(args.workload, rank, world, device)
-    N, Cin, Cout, pts = run.N, run.Cin, run.Cout, run.pts
-
+    # nvidia-smi attaching to the GPU stalls launches for milliseconds during its first second or so (a 16-cloud run
+    # showed single 3-5 ms steps when the sampler was started right before the warm-up; in steady state polling is
+    # harmless at any period, tools/sampler_probe.py): start it before the inputs are generated and uploaded
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()          # nvidia-smi needs ~0.1 s to start: begin before the warm-up steps
+        sampler.start()
+    run = Runner(args.workload, rank, world, device)
+    N, Cin, Cout, pts = run.N, run.Cin, run.Cout, run.pts
     warm = max(3, args.warmup)
     for _ in range(warm):
         run.step()
