@@ -34,7 +34,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -90,33 +89,34 @@ def peaks():
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi in loop mode writing to a temporary FILE, read back after the run: a reader thread in this process
+    wakes up on every sample and contends for the GIL with the thread that launches the kernels -- with the 5 ms switch
+    interval that showed up as single 8-20 ms steps in the short layer workloads."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
         self.proc = None
+        self.file = None
         self.lines = []
 
     def start(self):
+        import tempfile
         try:
+            self.file = tempfile.NamedTemporaryFile(prefix="conv3p_clocks_", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
+                 "-lms", "20"], stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def ready(self, timeout=3.0):
         """Block until the first sample arrived: nvidia-smi attaching to the GPU stalls launches for tens of ms, which
         must not fall into the timed region (a 16-cloud step showed 5.2 ms instead of 1.2 ms when it did)."""
         t0 = time.perf_counter()
-        while self.proc and not self.lines and time.perf_counter() - t0 < timeout and self.proc.poll() is None:
+        while (self.proc and os.path.getsize(self.file.name) == 0 and time.perf_counter() - t0 < timeout
+               and self.proc.poll() is None):
             time.sleep(0.01)
 
     def stop(self):
@@ -127,6 +127,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        try:
+            self.file.close()
+            with open(self.file.name) as fh:
+                self.lines = [ln.strip() for ln in fh]
+            os.unlink(self.file.name)
+        except OSError:
+            pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -453,7 +460,8 @@ def timed(fn, steps, world, device, finish=None):
     barrier(world)
     ms = e0.elapsed_time(e1)
     per = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
-    timed.last = {"median_ms": float(np.median(per)), "best_ms": float(min(per)), "worst_ms": float(max(per))}
+    timed.last = {"median_ms": float(np.median(per)), "best_ms": float(min(per)), "worst_ms": float(max(per)),
+                  "worst_step_index": int(np.argmax(per))}
     if world > 1:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -591,6 +599,20 @@ def gpu_arm(args):
     warm = max(3, args.warmup)
     for _ in range(warm):
         run.step()
+    run.join()
+    # Untimed settling steps on top of the W warm-up steps: the caching allocator keeps growing for a few steps when
+    # buffers are handed between streams (plan buffer, side-stream prefetch), and a cudaMalloc of a few hundred MB
+    # inside the timed region showed up as single 3-20 ms steps of the short layer workloads.  Run until the reserved
+    # pool has not changed for three steps (at most 20 more).
+    settled, reserved = 0, torch.cuda.memory_reserved(device)
+    for _ in range(20):
+        run.step()
+        torch.cuda.synchronize(device)
+        now = torch.cuda.memory_reserved(device)
+        settled = settled + 1 if now == reserved else 0
+        reserved = now
+        if settled >= 3:
+            break
     run.join()
     if rank == 0:
         sampler.ready()
