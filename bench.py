@@ -603,10 +603,10 @@ def gpu_arm(args):
     # Untimed settling steps on top of the W warm-up steps: the caching allocator keeps growing for a few steps when
     # buffers are handed between streams (plan buffer, side-stream prefetch), and a cudaMalloc of a few hundred MB
     # inside the timed region showed up as single 3-20 ms steps of the short layer workloads.  Run until the reserved
-    # pool has not changed for three steps (at most 20 more).
+    # pool has not changed for three steps (at most 20 more).  Without the collective: the count differs per rank.
     settled, reserved = 0, torch.cuda.memory_reserved(device)
     for _ in range(20):
-        run.step()
+        run.step(collective=False)
         torch.cuda.synchronize(device)
         now = torch.cuda.memory_reserved(device)
         settled = settled + 1 if now == reserved else 0
