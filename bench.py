@@ -899,7 +899,8 @@ def net_arm(args, rank, world, device):
         launch_count(reset=True)
         ms = timed(step, args.steps, world, device)
         res["shared_plans" if sharing else "plan_per_layer"] = {
-            "ms_per_step": ms, "value": per_gpu * world * N / (ms * 1e-3), "gpu_launches": launch_count() // args.steps}
+            "ms_per_step": ms, "value": per_gpu * world * N / (ms * 1e-3), "gpu_launches": launch_count() // args.steps,
+            "step_spread_rank0": dict(timed.last)}
     nets.SHARE_PLANS = True
     if rank != 0:
         if world > 1:
