@@ -445,19 +445,27 @@ def barrier(world):
 
 def timed(fn, steps, world, device, finish=None):
     """ms per step: barrier + synchronize on both sides, CUDA events on the current stream, max over ranks."""
+    import gc
     import torch
     import torch.distributed as dist
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]     # one record per step: median and best
-    e0.record()
-    for i in range(steps):
-        fn()
-        marks[i].record()
-    if finish:
-        finish()
-    e1.record()
-    barrier(world)
+    # no cyclic garbage collection inside the timed region: a generation-2 pass over the interpreter's heap (torch,
+    # numpy, the oracle bindings) is a 10-30 ms host pause, which showed up as single slow steps early in the region
+    gc.collect()
+    gc.disable()
+    try:
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]     # one record per step: median and best
+        e0.record()
+        for i in range(steps):
+            fn()
+            marks[i].record()
+        if finish:
+            finish()
+        e1.record()
+        barrier(world)
+    finally:
+        gc.enable()
     ms = e0.elapsed_time(e1)
     per = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     timed.last = {"median_ms": float(np.median(per)), "best_ms": float(min(per)), "worst_ms": float(max(per)),
