@@ -89,7 +89,9 @@ def peaks():
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi in loop mode writing to a temporary FILE, read back after the run: a reader thread in this process
+    """nvidia-smi in loop mode (one sample per 100 ms: the recipe's own line uses 200 ms; the GPU is under load from the
+    warm-up steps on, so a timed region shorter than the period is still represented) writing to a temporary FILE, read
+    back after the run: a reader thread in this process
     wakes up on every sample and contends for the GIL with the thread that launches the kernels -- with the 5 ms switch
     interval that showed up as single 8-20 ms steps in the short layer workloads."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -107,7 +109,7 @@ class ClockSampler:
             self.file = tempfile.NamedTemporaryFile(prefix="conv3p_clocks_", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=self.file, stderr=subprocess.DEVNULL)
+                 "-lms", "100"], stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
