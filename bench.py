@@ -610,26 +610,31 @@ def gpu_arm(args):
     for _ in range(warm):
         run.step()
     run.join()
-    # Untimed settling steps on top of the W warm-up steps: the caching allocator keeps growing for a few steps when
-    # buffers are handed between streams (plan buffer, side-stream prefetch), and a cudaMalloc of a few hundred MB
-    # inside the timed region showed up as single 3-20 ms steps of the short layer workloads.  Run until the reserved
-    # pool has not changed for three steps (at most 20 more).  Without the collective: the count differs per rank.
-    settled, reserved = 0, torch.cuda.memory_reserved(device)
-    for _ in range(20):
-        run.step(collective=False)
+    # Untimed rehearsal on top of the W warm-up steps.  The host enqueues many steps ahead of the GPU, and buffers that
+    # were handed to a side stream (the plan buffer, for the backward-list prefetch) can only be reused once that
+    # stream's event has completed -- so the caching allocator needs a deeper pool the further the host runs ahead, and
+    # it grows it with cudaMalloc (tens of ms for half a GB) at whatever step that happens: single 15-45 ms steps inside
+    # the timed region.  Rehearse the timed loop itself (same number of steps, no synchronisation inside) until a whole
+    # rehearsal needed no new device allocation (at most four).  Without the collective: the count differs per rank.
+    def device_allocs():
+        return torch.cuda.memory_stats(device).get("num_device_alloc", 0)
+
+    for _ in range(4):
+        before = device_allocs()
+        for _ in range(args.steps):
+            run.step(collective=False)
         torch.cuda.synchronize(device)
-        now = torch.cuda.memory_reserved(device)
-        settled = settled + 1 if now == reserved else 0
-        reserved = now
-        if settled >= 3:
+        if device_allocs() == before:
             break
     run.join()
     if rank == 0:
         sampler.ready()
     # the reported step time is taken WITHOUT the per-kernel event pairs (two cudaEventRecord per launch open small gaps
     # between dependent kernels); the per-kernel breakdown comes from a second, instrumented pass over the same steps
+    allocs0 = device_allocs()
     ms_step = timed(run.step, args.steps, world, device, finish=run.join)
     step_spread = dict(timed.last)
+    step_spread["device_mallocs_in_timed_region"] = device_allocs() - allocs0
     clocks = sampler.stop() if rank == 0 else None
     ms_profiled, launches, kern = profile_kernels(L, run.step, args.steps, world, device, finish=run.join)
     value = run.B_global * N / (ms_step * 1e-3)
