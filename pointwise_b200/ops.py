@@ -225,6 +225,13 @@ class NeighborPlan:
         self._stats = None
         self._stats_event = None
         self._stats_slot = None
+        # Side streams that read or write the plan buffer (deferred counters, backward-list prefetch) leave their events
+        # here; __del__ makes the ALLOCATING stream wait for them before the buffer goes back to the caching allocator.
+        # (Tensor.record_stream would do the same job lazily -- but then a buffer can only be reused once the
+        # allocator has SEEN the event complete, and a host that enqueues many steps ahead makes the pool grow by one
+        # plan buffer per step in flight: half-GB cudaMallocs, 15-45 ms each, at arbitrary steps.)
+        self._alloc_stream = torch.cuda.current_stream(self.device)
+        self._side_events = []
         L = _lib.lib()
         self._key = key = (self.B, self.N, self.stride, self.voxel_size)
         pts = self.B * self.N
@@ -286,10 +293,15 @@ class NeighborPlan:
                                                             C.c_void_p(side.cuda_stream)))
         self._stats_event = torch.cuda.Event()
         self._stats_event.record(side)
-        self.buffer.record_stream(side)
+        self._side_events.append(self._stats_event)
         _pending_checks.append(weakref.ref(self))
 
     def __del__(self):
+        try:      # the buffer is released in the allocating stream's order: that stream waits for the side streams first
+            for ev in getattr(self, "_side_events", ()):
+                self._alloc_stream.wait_event(ev)
+        except Exception:      # interpreter shutdown, CUDA context already gone
+            pass
         slot = getattr(self, "_stats_slot", None)
         if slot is not None:
             ev = getattr(self, "_stats_event", None)
@@ -402,7 +414,7 @@ class NeighborPlan:
                 self.geom, _ptr(self.points), _ptr(self.buffer), self.buffer.numel(), C.c_void_p(side.cuda_stream)))
             self._bwd_ready = torch.cuda.Event()
             self._bwd_ready.record(side)
-        self.buffer.record_stream(side)
+        self._side_events.append(self._bwd_ready)
         self.points.record_stream(side)
         return self
 

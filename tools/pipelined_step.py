@@ -2,6 +2,9 @@
 pipeline that has the next batch on the device can build it on a side stream while batch i's gradient kernels run
 (the plan kernels are integer / issue-bound and fit next to the persistent tensor-core CTAs).  Measures the fwd+bwd
 step with and without that overlap; every step still builds exactly one plan inside the timed region.
+(The figures in profiles/r2_summary.md were taken before NeighborPlan released its buffer in the allocating stream's
+order: a plan built on a foreign stream, as here, is now serialised behind its predecessor's side-stream work, and this
+tool shows a loss at every size.  Kept as the record of the experiment.)
 usage: python tools/pipelined_step.py [workload]"""
 import json
 import os
