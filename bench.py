@@ -619,6 +619,11 @@ def gpu_arm(args):
     def device_allocs():
         return torch.cuda.memory_stats(device).get("num_device_alloc", 0)
 
+    if world > 1:                      # one rehearsal WITH the collective, the same number of steps on every rank
+        for _ in range(args.steps):
+            run.step()
+        run.join()
+        torch.cuda.synchronize(device)
     for _ in range(4):
         before = device_allocs()
         for _ in range(args.steps):
